@@ -1,0 +1,180 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference,
+native ops compiled from its own sources by oracle/build_ref.py) on seeded synthetic inputs.
+Only runnable in the build container; the fixtures it writes are committed.
+
+    python tests/golden/make_golden.py
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refload  # noqa: E402
+from step_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+R = refload.load()
+T = torch.from_numpy
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def gen_nms():
+    rs = np.random.RandomState(7)
+    cases = {}
+    def add(name, b, s, thr):
+        b = np.asarray(b, np.float32).reshape(-1, 4); s = np.asarray(s, np.float32)
+        keep = R._C.nms(T(b), T(s), float(thr)).numpy()
+        cases[name + "_boxes"] = b; cases[name + "_scores"] = s
+        cases[name + "_thr"] = np.float32(thr); cases[name + "_keep"] = keep.astype(np.int64)
+    add("iou_eq_thr", [[0, 0, 9, 9], [0, 0, 9, 4]], [.9, .8], 0.5)           # IoU == thr -> suppressed (>=)
+    add("four", [[0, 0, 10, 10], [1, 1, 11, 11], [50, 50, 60, 60], [0, 0, 10, 10]], [.9, .8, .7, .95], 0.4)
+    add("third", [[0, 0, 2, 0], [0, 0, 0, 0]], [.9, .8], 1.0 / 3.0)          # IoU = 1/3 vs float32(1/3)
+    add("empty", np.zeros((0, 4)), np.zeros((0,)), 0.4)
+    add("single", [[3, 4, 50, 60]], [.1], 0.4)
+    for n in (63, 64, 65, 129, 1000):
+        x1 = rs.uniform(0, 150, n); y1 = rs.uniform(0, 150, n)
+        w = rs.uniform(20, 120, n); h = rs.uniform(20, 120, n)
+        b = np.stack([x1, y1, np.minimum(x1 + w, 223), np.minimum(y1 + h, 223)], 1)
+        s = rs.permutation(n).astype(np.float32) / n   # unique scores: torch.sort is not stable on ties
+        add("rand%d" % n, b, s, 0.4)
+    # integer-coordinate boxes produce many exact IoU ties at the threshold
+    b = rs.randint(0, 40, (300, 2)); wh = rs.randint(1, 30, (300, 2))
+    add("intgrid", np.concatenate([b, b + wh], 1), rs.permutation(300).astype(np.float32), 0.5)
+    np.savez_compressed(os.path.join(OUT, "nms_cases.npz"), **cases)
+    print("nms cases:", len(cases) // 4)
+
+
+def gen_roi_align():
+    rs = np.random.RandomState(11)
+    K, C, H, W = 3, 5, 14, 14
+    feat = rs.randn(K, C, H, W).astype(np.float32)
+    rois = [
+        [0, 10, 10, 10.5, 10.2],          # < 1 px after scaling: forced 1x1
+        [1, -40, -40, 60, 60],            # partly outside (samples < -1 -> 0)
+        [2, 100, 100, 400, 400],          # runs past the far edge
+        [2, 0, 0, 223, 223],              # whole map, grid 2x2
+        [0, 0, 0, 111, 55],               # non-integer bin, adaptive grid 1..
+        [1, 30.3, 17.7, 199.1, 222.9],
+        [2, 223, 223, 223, 223],          # last pixel
+        [0, 5, 5, 5, 5],
+    ]
+    for _ in range(40):
+        x1, y1 = rs.uniform(-30, 200, 2); w, h = rs.uniform(0, 220, 2)
+        rois.append([rs.randint(0, K), x1, y1, x1 + w, y1 + h])
+    rois = np.asarray(rois, np.float32)
+    out = {"feat": feat, "rois": rois}
+    for sr in (0, 2):
+        out["out_sr%d" % sr] = R._C.roi_align_forward(T(feat), T(rois), 1.0 / 16.0, 7, 7, sr).numpy()
+    out["out_3x5_s0p5"] = R._C.roi_align_forward(T(feat), T(rois * np.array([1, .1, .1, .1, .1], np.float32)),
+                                                 0.5, 3, 5, 0).numpy()
+    np.savez_compressed(os.path.join(OUT, "roi_align_cases.npz"), **out)
+    print("roi_align rois:", rois.shape[0])
+
+
+def gen_tubes():
+    rs = np.random.RandomState(3)
+    tu = R.tube_utils
+    out = {}
+    anchors = np.concatenate([rs.uniform(0, 150, (64, 2)), rs.uniform(150, 223, (64, 2))], 1).astype(np.float32)
+    deltas = (rs.randn(64, 4) * np.array([.2, .2, .5, .5])).astype(np.float32)
+    deltas[0, 2:] = [6.0, -6.0]; deltas[1, 2:] = [20.0, 0.0]   # large dw
+    out["dec_anchors"], out["dec_deltas"] = anchors, deltas
+    out["dec_out"] = tu.decode_coef(T(anchors), T(deltas)).numpy()
+    gt = anchors + rs.uniform(-5, 5, anchors.shape).astype(np.float32)
+    out["enc_gt"] = gt; out["enc_out"] = tu.encode_coef(T(gt), T(anchors)).numpy()
+    tubes = (rs.uniform(-20, 260, (9, 4, 2))).astype(np.float32)
+    tubes = np.concatenate([tubes, tubes + rs.uniform(-3, 120, (9, 4, 2)).astype(np.float32)], 2)
+    tubes[0, 0] = [10, 10, 12, 40]; tubes[1, 1] = [50, 50, 40, 90]   # degenerate -> whole image
+    out["val_in"] = tubes
+    out["val_out_224"] = tu.valid_tubes(tubes.copy(), width=224, height=224)
+    out["val_out_400"] = tu.valid_tubes(tubes.copy())
+    for Tt in (2, 3, 4):
+        t = tubes[:, :Tt].copy()
+        out["ext_in_T%d" % Tt] = t
+        out["ext_out_T%d" % Tt] = tu.extrapolate_tubes(t.copy(), Tt)
+    lst = [tubes[:2].copy(), np.zeros((0, 4, 4), np.float32), tubes[2:5].copy()]
+    flat, nums = tu.flatten_tubes(lst, batch_idx=True)
+    out["flat_out"], out["flat_nums"] = flat, np.asarray(nums)
+    out["extend_out"] = tu.extend_tubes(T(flat), 1.2, 224, 224).numpy()
+    np.savez_compressed(os.path.join(OUT, "tubes_cases.npz"), **out)
+    print("tubes ok")
+
+
+def build_nets(cfg, n_heads, context=False):
+    nets = {"base_net": quiet(R.models.BaseNet, cfg), "roi_net": R.models.ROINet(cfg.pool_mode, cfg.pool_size)}
+    nets["base_net"].load_state_dict(synth.base_net_state_dict()); nets["base_net"].eval()
+    for i in range(n_heads):
+        h = quiet(R.models.TwoBranchNet, cfg)
+        h.load_state_dict(synth.head_state_dict(100 + i, cfg), strict=True)
+        h.eval(); h.set_device("cpu")
+        nets["det_net%d" % i] = h
+    if context:
+        c = quiet(R.models.ContextNet, cfg)
+        c.load_state_dict(synth.context_net_state_dict(), strict=True); c.eval()
+        nets["context_net"] = c
+    return nets
+
+
+def run_pipeline(name, cfg, B, T_in, HW, N, context=False, store_feat=True):
+    nets = build_nets(cfg, cfg.max_iter, context)
+    x = synth.make_clips(B, T_in, HW, HW)
+    tubes = synth.make_proposals(B, N, cfg.T * cfg.NUM_CHUNKS[1], HW, HW)
+    out = {"B": B, "T_in": T_in, "HW": HW, "N": N}
+    with torch.no_grad():
+        cf = nets["base_net"](x)
+        ctx = nets["context_net"](cf) if context else None
+        # .clone(): on CPU the reference's valid_tubes mutates history['pred_loc'] in place through
+        # the shared numpy view (utils.py:107-121); the GPU path (.cpu() copies) does not.  We
+        # record the un-mutated GPU semantics by re-running decode below from the trajectory.
+        hist, traj = R.utils.inference(cfg, cf, ctx, nets, cfg.max_iter, [t.copy() for t in tubes])
+    if store_feat:
+        out["conv_feat"] = cf.numpy()
+    else:
+        out["conv_feat_sub"] = cf.numpy()[:, ::4, ::13, ::6, ::6].copy()
+    out["conv_feat_absmean"] = np.float64(cf.abs().double().mean().item())
+    if context:
+        out["context_feat"] = ctx.numpy()
+    for i, h in enumerate(hist):
+        out["prob%d" % i] = h["pred_prob"][:, 0].numpy().copy()
+        out["loc_valid%d" % i] = h["pred_loc"].numpy().copy()     # == valid_tubes(pred_loc) (CPU aliasing)
+        if h["pred_first_loc"] is not None:
+            out["first%d" % i] = h["pred_first_loc"].numpy().copy()
+            out["last%d" % i] = h["pred_last_loc"].numpy().copy()
+        out["nums%d" % i] = np.asarray(h["tubes_nums"])
+        out["traj%d" % i] = np.concatenate([t[0] for t in traj[i]], 0)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "conv_feat", tuple(cf.shape), "absmean %.4f" % cf.abs().mean().item())
+
+
+def gen_pipelines():
+    # C1 (BASELINE.json configs[0]): 1 clip, T=8, 112x112, 1 proposal, max_iter=1
+    run_pipeline("pipe_c1", synth.make_cfg(T=2, max_iter=1, NUM_CHUNKS={1: 1}, image_size=(112, 112)),
+                 B=1, T_in=8, HW=112, N=1)
+    # spatial mode, 3 steps, 2 clips x 5 proposals, T'=4
+    run_pipeline("pipe_spatial", synth.make_cfg(T=4, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 1}, image_size=(112, 112)),
+                 B=2, T_in=16, HW=112, N=5)
+    # temporal mode (tube extension 1 -> 3 chunks at step 3), T=3, T'=9.  The reference's slicing
+    # (two_branch.py:265-270) only works for odd T when chunks > 1; its shipped config is T=3.
+    for mode in ("predict", "extrapolate", "mean"):
+        run_pipeline("pipe_temporal_" + mode,
+                     synth.make_cfg(T=3, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 3}, temporal_mode=mode,
+                                    image_size=(112, 112)),
+                     B=2, T_in=36, HW=112, N=4, store_feat=(mode == "predict"))
+    # native AVA shape with ContextNet (only valid at 400x400, two_branch.py:127): 1 clip, 3 proposals
+    run_pipeline("pipe_ava_context",
+                 synth.make_cfg(T=3, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 3}, no_context=False,
+                                image_size=(400, 400)),
+                 B=1, T_in=36, HW=400, N=3, context=True, store_feat=False)
+
+
+if __name__ == "__main__":
+    gen_nms(); gen_roi_align(); gen_tubes(); gen_pipelines()

@@ -1,0 +1,126 @@
+"""CPU: pins oracle/ (C restatement + torch-CPU restatement) against the committed golden vectors
+that tests/golden/make_golden.py produced by running the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as om
+from oracle import ops, tubes
+from step_b200 import synth
+
+NMS_CASES = ["iou_eq_thr", "four", "third", "empty", "single", "rand63", "rand64", "rand65", "rand129",
+             "rand1000", "intgrid"]
+
+
+@pytest.mark.parametrize("name", NMS_CASES)
+def test_nms_oracle_matches_reference(golden, name):
+    g = golden("nms_cases")
+    keep = ops.nms(g[name + "_boxes"], g[name + "_scores"], float(g[name + "_thr"]))
+    assert keep.dtype == np.int64
+    assert np.array_equal(keep, g[name + "_keep"])
+
+
+def test_nms_known_answers():
+    # SURVEY.md appendix A probes of the reference
+    b = np.array([[0, 0, 10, 10], [1, 1, 11, 11], [50, 50, 60, 60], [0, 0, 10, 10]], np.float32)
+    assert ops.nms(b, np.array([.9, .8, .7, .95], np.float32), 0.4).tolist() == [2, 3]
+    b = np.array([[0, 0, 9, 9], [0, 0, 9, 4]], np.float32)
+    s = np.array([.9, .8], np.float32)
+    assert ops.nms(b, s, 0.5, ge=True).tolist() == [0]       # cpu/nms_cpu.cpp:84  '>='
+    assert ops.nms(b, s, 0.5, ge=False).tolist() == [0, 1]   # cuda/nms.cu:84      '>'
+    # tie on scores: our contract is (score desc, index asc); torch.sort is unstable for n > 16
+    b = np.array([[0, 0, 9, 9], [1, 1, 10, 10], [100, 100, 110, 110]], np.float32)
+    assert ops.nms(b, np.full(3, .5, np.float32), 0.4).tolist() == [0, 2]
+
+
+def test_roi_align_oracle_bit_exact(golden):
+    g = golden("roi_align_cases")
+    for sr in (0, 2):
+        out = ops.roi_align_fwd(g["feat"], g["rois"], 1.0 / 16.0, 7, 7, sr)
+        assert np.array_equal(out, g["out_sr%d" % sr])
+    rois = g["rois"] * np.array([1, .1, .1, .1, .1], np.float32)
+    assert np.array_equal(ops.roi_align_fwd(g["feat"], rois, 0.5, 3, 5, 0), g["out_3x5_s0p5"])
+
+
+def test_roi_align_bwd_is_adjoint_of_fwd(golden):
+    g = golden("roi_align_cases")
+    feat, rois = g["feat"], g["rois"]
+    K, C, H, W = feat.shape
+    rs = np.random.RandomState(0)
+    gout = rs.randn(rois.shape[0], C, 7, 7).astype(np.float32)
+    gin = ops.roi_align_bwd(gout, rois, 1 / 16., 7, 7, K, C, H, W, 0)
+    lhs = float((ops.roi_align_fwd(feat, rois, 1 / 16., 7, 7, 0).astype(np.float64) * gout).sum())
+    rhs = float((feat.astype(np.float64) * gin).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_roi_pool_properties():
+    rs = np.random.RandomState(1)
+    feat = rs.randn(2, 3, 14, 14).astype(np.float32)
+    rois = np.array([[0, 0, 0, 223, 223], [1, 16, 16, 47, 47], [1, 500, 500, 600, 600]], np.float32)
+    out, arg = ops.roi_pool_fwd(feat, rois, 1 / 16., 7, 7)
+    # whole-map ROI: rounded to [0,14] -> 15 wide, bins cover every cell; global max is present
+    assert np.isclose(out[0].max(axis=(1, 2)), feat[0].max(axis=(1, 2))).all()
+    # argmax indexes the value it reports
+    flat = feat[1].reshape(3, -1)
+    for c in range(3):
+        assert np.array_equal(out[1, c].ravel(), flat[c][arg[1, c].ravel()])
+    # empty region -> 0 and argmax -1  (ROIPool_cuda.cu:78-84)
+    assert (out[2] == 0).all() and (arg[2] == -1).all()
+    gin = ops.roi_pool_bwd(np.ones_like(out), arg, rois, 7, 7, 2, 3, 14, 14)
+    assert gin.sum() == (arg != -1).sum()
+
+
+def test_tube_ops_match_reference(golden):
+    g = golden("tubes_cases")
+    dec = tubes.decode_coef(g["dec_anchors"], g["dec_deltas"],
+                            exp=lambda v: torch.exp(torch.from_numpy(np.ascontiguousarray(v))).numpy())
+    assert np.array_equal(dec, g["dec_out"])
+    assert np.allclose(tubes.encode_coef(g["enc_gt"], g["dec_anchors"]), g["enc_out"], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(tubes.valid_tubes(g["val_in"], 224, 224), g["val_out_224"])
+    assert np.array_equal(tubes.valid_tubes(g["val_in"]), g["val_out_400"])
+    for T in (2, 3, 4):
+        assert np.array_equal(tubes.extrapolate_tubes(g["ext_in_T%d" % T], T), g["ext_out_T%d" % T])
+    lst = [g["val_in"][:2], np.zeros((0, 4, 4), np.float32), g["val_in"][2:5]]
+    flat, nums = tubes.flatten_tubes(lst, batch_idx=True)
+    assert np.array_equal(flat, g["flat_out"]) and nums == g["flat_nums"].tolist()
+    assert np.array_equal(tubes.extend_tubes(flat, 1.2, 224, 224), g["extend_out"])
+
+
+PIPES = {
+    "pipe_c1": dict(cfg=dict(T=2, max_iter=1, NUM_CHUNKS={1: 1}, image_size=(112, 112))),
+    "pipe_spatial": dict(cfg=dict(T=4, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 1}, image_size=(112, 112))),
+    "pipe_temporal_predict": dict(cfg=dict(T=3, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 3},
+                                           temporal_mode="predict", image_size=(112, 112))),
+    "pipe_temporal_extrapolate": dict(cfg=dict(T=3, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 3},
+                                               temporal_mode="extrapolate", image_size=(112, 112))),
+    "pipe_temporal_mean": dict(cfg=dict(T=3, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 3},
+                                        temporal_mode="mean", image_size=(112, 112))),
+}
+
+
+@pytest.mark.parametrize("name", list(PIPES))
+def test_pipeline_oracle_matches_reference(golden, name):
+    """Same torch CPU backend + same thread count => the restatement must be bit-identical to the
+    reference modules; allow 1e-5 rel for a different host thread count."""
+    g = golden(name)
+    cfg = synth.make_cfg(**PIPES[name]["cfg"])
+    B, T_in, HW, N = int(g["B"]), int(g["T_in"]), int(g["HW"]), int(g["N"])
+    x = synth.make_clips(B, T_in, HW, HW)
+    with torch.no_grad():
+        cf = om.base_net(x, synth.base_net_state_dict())
+        tol = dict(rtol=1e-4, atol=1e-4)
+        if "conv_feat" in g:
+            assert np.allclose(cf.numpy(), g["conv_feat"], **tol)
+        heads = [synth.head_state_dict(100 + i, cfg) for i in range(cfg.max_iter)]
+        tb = synth.make_proposals(B, N, cfg.T * cfg.NUM_CHUNKS[1], HW, HW)
+        hist, traj = om.inference(cfg, cf, None, heads, cfg.max_iter, tb)
+    for i, h in enumerate(hist):
+        assert np.allclose(h["pred_prob"][:, 0].numpy(), g["prob%d" % i], rtol=1e-4, atol=1e-5)
+        # the reference's CPU history['pred_loc'] is aliased and mutated by valid_tubes
+        # (utils.py:107-121) except at a step that extends the tubes (cat/extrapolate make a copy)
+        extends = i + 1 < cfg.max_iter and cfg.NUM_CHUNKS[i + 2] == cfg.NUM_CHUNKS[i + 1] + 2
+        v = h["pred_loc"].numpy() if extends else tubes.valid_tubes(h["pred_loc"].numpy(), HW, HW)
+        assert np.allclose(v, g["loc_valid%d" % i], rtol=1e-4, atol=1e-3)
+        assert h["tubes_nums"] == g["nums%d" % i].tolist()
+        assert np.allclose(np.concatenate([t[0] for t in traj[i]], 0), g["traj%d" % i], rtol=1e-4, atol=1e-3)
