@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- STEP inference throughput (clips/s) on B200, BASELINE.json config 4.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic clips: I3D trunk -> (ROIAlign ->
+two-branch head -> tube update) x max_iter=3, B=8 clips per GPU, T=32, 224x224, 11 proposals/clip,
+fp16 storage / fp32 accumulate.  Clips are independent, so N GPUs each take their own 8 clips
+(weak scaling, no data-path collective) and the fixed-shape detections are gathered once per batch
+over NCCL.  Prints ONE JSON line (contract in the task brief).
+
+value : clips/s with the batch already resident in HBM (device-timed, max over ranks).
+e2e   : same call through the public API with pinned-host clips: H2D of the batch and D2H of the
+        last step's scores/boxes inside the timed region.
+roofline : the dominant kernel class (conv_umma_kernel, tcgen05 implicit GEMM): algorithmic conv
+        FLOPs of one step (362.06 GFLOP/clip) / the device time of exactly those
+        launches replayed back-to-back, against MEASURED_PEAKS.json's sustained bf16 figure.
+cpu_baseline : the oracle port (oracle/model.py, torch-CPU fp32 == the reference's arithmetic) on
+        this box's host cores on a bounded sample (1 clip per timed pass).
+--impl reference : the same oracle timed as the reference arm (its own CPU implementation of the path).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_GFLOP_PER_CLIP = 362.06          # SURVEY.md section 8d / BASELINE.md section 3 (trunk 109.29 + 3 x 84.26)
+WORKLOAD = dict(B=8, T_in=32, HW=224, N=11, max_iter=3)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", 1451.1), hbm=d.get("hbm_gbs", 6586.1), src="measured")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_nets(cfg, device):
+    import step_b200
+    from step_b200 import synth
+    nets = {"base_net": step_b200.BaseNet(cfg), "roi_net": step_b200.ROINet(cfg.pool_mode, cfg.pool_size)}
+    nets["base_net"].load_state_dict(synth.base_net_state_dict())
+    for i in range(cfg.max_iter):
+        h = step_b200.TwoBranchNet(cfg)
+        h.load_state_dict(synth.head_state_dict(100 + i, cfg))
+        nets["det_net%d" % i] = h
+    for k in nets:
+        nets[k] = nets[k].to(device).eval()
+        if hasattr(nets[k], "set_device"):
+            nets[k].set_device(device)
+    return nets
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import step_b200
+    from step_b200 import _lib, engine, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = WORKLOAD
+    cfg = synth.make_cfg(fp16=True, T=W["T_in"] // 4, max_iter=W["max_iter"], NUM_CHUNKS={1: 1, 2: 1, 3: 1},
+                         image_size=(W["HW"], W["HW"]))
+    nets = build_nets(cfg, dev)
+    B = W["B"]
+    # rank r owns clips [r*B, (r+1)*B) of the synthetic stream (different seed per rank)
+    clips_host = synth.make_clips(B, W["T_in"], W["HW"], W["HW"], seed=1234 + rank).pin_memory()
+    clips_dev = clips_host.to(dev)
+    tubes = synth.make_proposals(B, W["N"], cfg.T, W["HW"], W["HW"])
+    out_host = {"p": torch.empty((B * W["N"], cfg.num_classes), dtype=torch.float32).pin_memory(),
+                "l": torch.empty((B * W["N"], cfg.T, 4), dtype=torch.float32).pin_memory()}
+    gather = None
+    if world > 1:
+        gather = torch.empty((world, B * W["N"], cfg.num_classes + 4), dtype=torch.float32, device=dev)
+
+    def step(x_dev):
+        with torch.no_grad():
+            cf = nets["base_net"](x_dev)
+            hist, _ = step_b200.inference(cfg, cf, None, nets, cfg.max_iter, tubes, want_trajectory=False)
+        last = hist[-1]
+        if gather is not None:  # one NCCL all_gather of the fixed-shape detections per batch
+            det = torch.cat([last["pred_prob"][:, 0], last["pred_loc"][:, cfg.T // 2]], dim=1).contiguous()
+            dist.all_gather_into_tensor(gather.view(-1, det.shape[1]), det)
+        return last
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def e2e_step():
+        x = clips_host.to(dev, non_blocking=True)
+        last = step(x)
+        out_host["p"].copy_(last["pred_prob"][:, 0], non_blocking=True)
+        out_host["l"].copy_(last["pred_loc"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the detections every batch
+
+    for _ in range(args.warmup):
+        step(clips_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(lambda: step(clips_dev), args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # roofline of the dominant kernel class: replay exactly the conv launches of one step
+    roof = None
+    if rank == 0:
+        rec = []
+        engine.RECORDER = rec
+        try:
+            step(clips_dev)
+        finally:
+            engine.RECORDER = None
+        torch.cuda.synchronize()
+        real_lib = _lib.lib()
+
+        def replay():
+            s = _lib.stream()
+            for q, _ in rec:
+                _lib.check(real_lib.step_conv3d_fwd(q, s))
+        replay()
+        ms_conv = timed_local(torch, replay, max(3, args.steps))
+        pk = peaks()
+        flops = ALG_GFLOP_PER_CLIP * 1e9 * B
+        achieved = flops / (ms_conv / max(3, args.steps) * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_umma_kernel", "achieved": round(achieved, 2),
+                "peak": pk["tflops"], "peak_source": pk["src"] + " bf16 sustained", "unit": "TFLOP/s",
+                "frac": round(achieved / pk["tflops"], 4), "traffic": None,
+                "launches_per_step": len(rec), "ms_per_step_in_kernel": round(ms_conv / max(3, args.steps), 4),
+                "algorithmic_gflop_per_step": round(flops / 1e9, 1)}
+        del rec
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = ms / args.steps
+    total_clips = world * B * args.steps
+    cpu = cpu_baseline(sample_clips=1, passes=2)
+    line = {
+        "metric": "clips/sec (T=32,224x224) STEP max_iter=3", "value": round(total_clips / (ms * 1e-3), 3),
+        "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "C4: full STEP inference, two_branch, 11 proposals, max_iter=3, batch 8/GPU, "
+                               "T=32, 224x224 (BASELINE.json configs[3])", "batch_per_gpu": B,
+                   "global_batch": B * world, "proposals": W["N"], "l2": "inputs+activations > L2 (batch = 154 MB fp32)",
+                   "a_mode": os.environ.get("STEP_B200_AMODE", "box"), "parallelism": "clip-parallel x%d" % world},
+        "e2e": {"value": round(total_clips / (ms_e2e * 1e-3), 3), "unit": "clips/s",
+                "h2d_bytes_per_step": int(clips_host.numel() * 4),
+                "d2h_bytes_per_step": int(out_host["p"].numel() * 4 + out_host["l"].numel() * 4)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def timed_local(torch, fn, steps):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def oracle_pass(n_clips):
+    """The reference's own arithmetic (torch-CPU fp32 modules restated in oracle/model.py) on n clips
+    of the C4 shape: trunk + 3 refinement steps.  Returns seconds."""
+    import torch
+    from oracle import model as om
+    from step_b200 import synth
+    W = WORKLOAD
+    cfg = synth.make_cfg(fp16=False, T=W["T_in"] // 4, max_iter=W["max_iter"], NUM_CHUNKS={1: 1, 2: 1, 3: 1},
+                         image_size=(W["HW"], W["HW"]))
+    sd = synth.base_net_state_dict()
+    heads = [synth.head_state_dict(100 + i, cfg) for i in range(cfg.max_iter)]
+    x = synth.make_clips(n_clips, W["T_in"], W["HW"], W["HW"])
+    tubes = synth.make_proposals(n_clips, W["N"], cfg.T, W["HW"], W["HW"])
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        cf = om.base_net(x, sd)
+        om.inference(cfg, cf, None, heads, cfg.max_iter, tubes)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(sample_clips=1, passes=2):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle_pass(sample_clips)  # warm-up (oneDNN primitive creation)
+    ts = [oracle_pass(sample_clips) for _ in range(passes)]
+    best = sorted(ts)[len(ts) // 2]
+    return {"value": round(sample_clips / best, 4), "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": "%d clip(s) of the C4 shape (T=32, 224x224, 11 proposals, 3 steps), fp32 torch-CPU oracle, "
+                      "median of %d passes after 1 warm-up" % (sample_clips, passes)}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port -- the reference's
+    Python cannot travel to the GPU box; oracle/model.py is bit-identical to it in the build container)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(min(args.warmup, 1)):
+        oracle_pass(1)
+    steps = min(args.steps, 5)
+    t = sum(oracle_pass(1) for _ in range(steps))
+    v = round(steps / t, 4)
+    print(json.dumps({
+        "impl": "reference", "metric": "clips/sec (T=32,224x224) STEP max_iter=3", "value": v, "unit": "clips/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(t / steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4 shape, bounded sample: 1 clip per step (T=32, 224x224, 11 proposals, max_iter=3)"},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                         "sample": "1 clip per step, %d steps" % steps},
+        "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,175 @@
+/*
+ * step_b200.h -- C ABI of libstep_b200.so: the sm_100a implementation of the STEP hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes raw device
+ * pointers, plain sizes and an explicit cudaStream_t; none allocates, synchronises or touches
+ * the default stream, so each is CUDA-graph capturable.  Every entry returns 0 on success or a
+ * non-zero code (a cudaError_t, or STEP_E_* below); step_last_error() then describes it.
+ *
+ * Reference interface each group replaces (paths relative to the NVlabs/STEP tree):
+ *   nms            external/maskrcnn_benchmark/csrc/vision.cpp:31  _C.nms  (nms.h:34-51,
+ *                  cpu/nms_cpu.cpp:29-99, cuda/nms.cu:47-155)
+ *   roi_align_*    vision.cpp:32-33  _C.roi_align_forward/backward  (ROIAlign.h:35-69,
+ *                  cpu/ROIAlign_cpu.cpp:137-281, cuda/ROIAlign_cuda.cu:88-370)
+ *   roi_pool_*     vision.cpp:34-35  _C.roi_pool_forward/backward   (ROIPool.h:35-71,
+ *                  cuda/ROIPool_cuda.cu:40-226)
+ *   tube_*         utils/tube_utils.py:10-27,59-92,127-189,214-266 and the per-step host loop of
+ *                  utils/utils.py:61-129
+ *   conv / pool / linear / head_*   the torch.nn calls of models/i3dpt.py:43-163,
+ *                  models/networks.py:69-83, models/two_branch.py:60-111,132-138,223-274,337
+ *   clip_*         the permute + (apex) cast at models/networks.py:77
+ *
+ * Tensor conventions: activations are channels-last -- [N, T, H, W, C] ("NDHWC") with an explicit
+ * channel stride `ld` (elements) so a kernel can read or write a channel slice of a wider buffer
+ * (this is how Mixed's concat, i3dpt.py:162, and the local-branch concat, two_branch.py:256,
+ * disappear).  The *_nchw entry points take the reference's NCHW fp32 layout unchanged.
+ */
+#ifndef STEP_B200_H_
+#define STEP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* step_stream_t; /* == cudaStream_t */
+
+enum { STEP_F32 = 0, STEP_F16 = 1 };
+enum { STEP_OK = 0, STEP_E_ARG = 10001, STEP_E_UNSUPPORTED = 10002, STEP_E_WORKSPACE = 10003,
+       STEP_E_DRIVER = 10004 };
+
+int step_version(void);
+const char* step_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t step_launch_count(void);
+
+/* ------------------------------------------------------------------ NMS ------------------ */
+/* Greedy NMS, legacy "+1" areas, bit-exact with cpu/nms_cpu.cpp (ge=1: suppress when
+ * IoU >= thr) or cuda/nms.cu (ge=0: IoU > thr).  Order: score descending, original index
+ * ascending on ties.  keep_out receives the kept ORIGINAL indices in ascending order,
+ * *n_keep (device int) their count.  Fully device-resident (no host scan, no D2H). */
+size_t step_nms_workspace_bytes(int n);
+int step_nms_f32(const float* boxes /*[n,4]*/, const float* scores /*[n]*/, int n, float thr, int ge,
+                 int64_t* keep_out /*[n]*/, int* n_keep, void* workspace, size_t ws_bytes,
+                 step_stream_t stream);
+/* Many independent small problems in one launch (the per-clip x per-class loop of test.py:178-201):
+ * segment s = rows [seg_offsets[s], seg_offsets[s+1]); at most 1024 rows per segment.
+ * keep_mask[i] = 1 if row i survives NMS inside its segment.  Rows with score < min_score are
+ * dropped before NMS (test.py:183 confidence threshold; pass -INF to disable). */
+int step_nms_segmented_f32(const float* boxes, const float* scores, const int* seg_offsets, int n_seg,
+                           float thr, int ge, float min_score, uint8_t* keep_mask, step_stream_t stream);
+
+/* ------------------------------------------------------------------ ROI ops -------------- */
+/* Reference layout (NCHW fp32 in, [R,C,ph,pw] fp32 out), arithmetic order of the reference. */
+int step_roi_align_fwd_nchw_f32(const float* feat, int K, int C, int H, int W, const float* rois, int R,
+                                float scale, int ph, int pw, int sampling_ratio, float* out,
+                                step_stream_t stream);
+int step_roi_align_bwd_nchw_f32(const float* grad_out, const float* rois, int R, float scale, int ph,
+                                int pw, int K, int C, int H, int W, int sampling_ratio,
+                                float* grad_in /* zero-filled by the call */, step_stream_t stream);
+int step_roi_pool_fwd_nchw_f32(const float* feat, int K, int C, int H, int W, const float* rois, int R,
+                               float scale, int ph, int pw, float* out, int32_t* argmax,
+                               step_stream_t stream);
+int step_roi_pool_bwd_nchw_f32(const float* grad_out, const int32_t* argmax, const float* rois, int R,
+                               int ph, int pw, int K, int C, int H, int W,
+                               float* grad_in /* zero-filled by the call */, step_stream_t stream);
+/* Channels-last fast path: feat [K,H,W,C] (channel stride feat_ld), out [R,ph,pw,C] (channel
+ * stride out_ld).  dtype STEP_F32 / STEP_F16 (fp32 accumulation, same operation order as the
+ * reference; the fp32 variant is bit-identical to the NCHW one up to the permutation).
+ * C must be a multiple of 8 (f16) / 4 (f32); feat_ld, out_ld likewise.
+ * Frame map: ROI column 0 indexes frames of the slice conv_feat[:, t_start:t_start+roi_T]
+ * (utils/utils.py:48); with roi_T > 0 the kernel reads frame (f / roi_T) * feat_T + t_start + f % roi_T
+ * of the full map instead of needing the slice copied.  roi_T == 0: identity. */
+int step_roi_align_fwd_nhwc(const void* feat, int dtype, int K, int H, int W, int C, int feat_ld,
+                            const float* rois, int R, float scale, int ph, int pw, int sampling_ratio,
+                            void* out, int out_ld, int roi_T, int feat_T, int t_start, step_stream_t stream);
+int step_roi_pool_fwd_nhwc(const void* feat, int dtype, int K, int H, int W, int C, int feat_ld,
+                           const float* rois, int R, float scale, int ph, int pw, void* out, int out_ld,
+                           int roi_T, int feat_T, int t_start, step_stream_t stream);
+
+/* ------------------------------------------------------------------ tube arithmetic ------ */
+/* boxes are rows of 4 floats with a row stride (in floats) so the [.,5] flat-tube layout
+ * (frame index first, tube_utils.py:238) can be addressed in place. */
+int step_tube_decode_f32(const float* anchors, int anchor_stride, const float* deltas, int n, float* out,
+                         step_stream_t stream);                         /* tube_utils.py:165-189 */
+int step_tube_encode_f32(const float* gt, const float* anchors, int anchor_stride, int n, float* out,
+                         step_stream_t stream);                         /* tube_utils.py:143-163 */
+int step_tube_valid_f32(float* boxes /*in place, [n,4]*/, int n, float width, float height,
+                        step_stream_t stream);                          /* tube_utils.py:59-92 */
+int step_tube_extrapolate_f32(const float* tubes /*[n,L,4]*/, int n, int L, int T, float width,
+                              float height, float* out /*[n,L+2T,4]*/, step_stream_t stream); /* :10-27 */
+int step_tube_extend_f32(const float* tubes /*[n,5]*/, int n, float ratio, float width, float height,
+                         float* out /*[n,5]*/, step_stream_t stream);   /* tube_utils.py:248-266 */
+/* One launch for the whole between-steps host loop of utils/utils.py:61-129:
+ * decode (local, and first/last when mode==PREDICT) -> optional temporal extension
+ * (concat / extrapolate / mean) -> valid_tubes -> re-flatten with new frame indices.
+ * flat_in [R,L,5]; loc/first/last [R,L,4]/[R,T,4]/[R,T,4]; clip_of_tube [R] int32;
+ * pred_* are the history tensors; flat_out [R,L_out,5] with L_out = extend ? L+2T : L. */
+enum { STEP_EXT_NONE = 0, STEP_EXT_PREDICT = 1, STEP_EXT_EXTRAPOLATE = 2, STEP_EXT_MEAN = 3 };
+int step_tube_update_f32(const float* flat_in, const float* loc, const float* first, const float* last,
+                         const int32_t* clip_of_tube, int R, int L, int T, int decode_neighbors,
+                         int ext_mode, float width, float height, float* pred_loc, float* pred_first,
+                         float* pred_last, float* flat_out, step_stream_t stream);
+
+/* ------------------------------------------------------------------ layout --------------- */
+/* clip [N,T,Cc,H,W] fp32 (the layout BaseNet.forward receives, networks.py:69-76) ->
+ * channels-last [N,T,H,W,ld] in `dtype`, channels >= Cc zero-filled. */
+int step_clip_to_ndhwc(const float* clip, int N, int T, int Cc, int H, int W, void* out, int dtype, int ld,
+                       step_stream_t stream);
+/* Same input, space-to-depth by 2 in (T,H,W) for the stride-2 stem (i3dpt.py:184-189):
+ * out [N,T/2,H/2,W/2,ld] f16 with channel = ((rt*2+rh)*2+rw)*Cc + c. T,H,W must be even. */
+int step_clip_to_s2d_f16(const float* clip, int N, int T, int Cc, int H, int W, void* out, int ld,
+                         step_stream_t stream);
+/* channels-last [M, C] (stride ld) <-> planar [N, C, S] fp32, M = N*S (boundary conversions). */
+int step_nhwc_to_nchw_f32(const void* in, int dtype, int N, int S, int C, int ld, float* out,
+                          step_stream_t stream);
+int step_nchw_to_nhwc(const float* in, int N, int S, int C, void* out, int dtype, int ld,
+                      step_stream_t stream);
+
+/* ------------------------------------------------------------------ conv / pool / linear - */
+typedef struct {
+  int dtype;                 /* STEP_F32: SIMT fp32 path.  STEP_F16: tcgen05 implicit GEMM, fp32 accumulate */
+  int N, T, H, W;            /* input extent (pixels) */
+  int Cin, in_ld;            /* input channels read, channel stride of x */
+  int Cout, out_ld, out_coff;/* output channels, channel stride of y, first channel written in y */
+  int KT, KH, KW;            /* filter taps */
+  int ST, SH, SW;            /* strides (the f16 path supports stride 1 only; the stem uses s2d) */
+  int PT, PH, PW;            /* low-side zero padding (TF "SAME": i3dpt.py:14-31) */
+  int OT, OH, OW;            /* output extent */
+  int relu;                  /* apply max(.,0) last */
+  int w_ld;                  /* weight channel stride: w is [Cout, KT, KH, KW, w_ld] in `dtype` */
+  const void* x;
+  const void* w;
+  const float* scale;        /* per-Cout multiplier (folded BatchNorm, i3dpt.py:107) or NULL (=1) */
+  const float* shift;        /* per-Cout addend (folded BN shift / conv bias) or NULL (=0) */
+  const void* residual;      /* optional tensor added before relu (two_branch.py:79-81), layout of y */
+  int res_ld, res_coff;
+  void* y;
+  int a_mode;                /* f16 path: 0 auto, 1 linear (1x1x1 only), 2 box tiles, 3 TMA im2col */
+} step_conv_params;
+int step_conv3d_fwd(const step_conv_params* p, step_stream_t stream);
+
+/* MaxPool3dTFPadding (i3dpt.py:114-126): zero pad (low PT/PH/PW, high implied), ceil_mode. */
+int step_maxpool3d_fwd(const void* x, int dtype, int N, int T, int H, int W, int C, int in_ld, int KT,
+                       int KH, int KW, int ST, int SH, int SW, int PT, int PH, int PW, int pad_hi_t,
+                       int pad_hi_h, int pad_hi_w, int OT, int OH, int OW, void* y, int out_ld,
+                       step_stream_t stream);
+/* mean over axis B: x [A, B, P, C] (C contiguous, pixel stride ld) -> y [A, P*C] fp32/f16
+ * (the temporal mean of two_branch.py:249 taken before the classifier, which is linear). */
+int step_mean_mid(const void* x, int dtype, int A, int B, int P, int C, int ld, void* y, int out_dtype,
+                  step_stream_t stream);
+/* y[m, n] = act(sum_k x[m,k] * w[n,k] + bias[n]); small-N GEMM (N <= 64) for global_cls,
+ * local_reg, neighbor_reg (two_branch.py:246,261,269-270).  x [M,K] (row stride x_ld) in dtype,
+ * w [N,K] in dtype, y fp32 [M, y_ld].  act: 0 none, 1 sigmoid (applied after accumulation).
+ * accumulate != 0: y += result.  row_map (optional, device int32 [M]): x row read for output row m
+ * (the per-tube context gather of utils/utils.py:54-57). */
+int step_linear_small_n(const void* x, int dtype, int M, int K, int x_ld, const void* w, const float* bias,
+                        int N, float* y, int y_ld, int act, int accumulate, const int32_t* row_map,
+                        step_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEP_B200_H_ */

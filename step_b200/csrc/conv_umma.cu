@@ -1,0 +1,533 @@
+// conv_umma.cu -- channels-last 3-D / 2-D convolution as an implicit GEMM on the 5th-generation
+// tensor cores of sm_100a: TMA-staged operand tiles, tcgen05.mma with the accumulator in TMEM,
+// fused BatchNorm-scale/shift (+bias) + residual + ReLU epilogue that writes a channel slice of a
+// wider buffer (the Inception concat, models/i3dpt.py:157-163, never materialises).
+//
+// Replaces, for the fp16 path, every Conv3d/BatchNorm3d/ReLU triple of models/i3dpt.py:103-111 and
+// the Conv2d/ReLU/residual chains of models/two_branch.py:60-111,236,258.
+//
+// GEMM view:  D[M = output pixels, N = Cout] = A[M, K = taps x Cin] * B[K, N]
+//   A (activations, [N,T,H,W,Cin] fp16, K-major rows = pixels): one TMA load per (filter tap,
+//     channel block) into a 128-row swizzled tile.  Three addressing modes:
+//       LINEAR  1x1x1 filters: the tensor is a plain [M, Cin] matrix (2-D map), dense M tiles.
+//       BOX     k>1: the M tile is a (bw x bh x bt) box of output pixels; the tap shifts the box and
+//               TMA zero-fills out-of-bounds pixels == the TF-"SAME" zero halo (i3dpt.py:14-31).
+//       IM2COL  k>1: TMA im2col mode walks 128 consecutive output pixels (w->h->t->n) inside the
+//               padded bounding box; dense M tiles on any map size.
+//   B (weights, [Cout, taps, Cin] fp16, K-major rows = output channels): 3-D map, box (BK,1,BN).
+//   D: fp32 in TMEM, 128 lanes x BN columns.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> scale/shift/residual/relu -> fp16 -> global).
+// Pipeline: kStages smem stages, full/empty mbarriers; 2 CTAs per SM overlap one CTA's epilogue with
+// the other's main loop.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace step {
+
+enum { A_LINEAR = 1, A_BOX = 2, A_IM2COL = 3 };
+
+constexpr int kBM = 128;       // UMMA M (cta_group::1)
+constexpr int kMaxBN = 128;    // <= 128 TMEM columns per CTA so two CTAs share an SM
+constexpr int kStages = 3;
+constexpr int kThreads = 192;
+
+struct ConvGeom {
+  int mode;
+  int taps, KT, KH, KW, PT, PH, PW;
+  int kblocks_per_tap;          // ceil(Cin / BK)
+  int BN, n_tiles;              // N tile (multiple of 16) and count
+  int Cout, out_ld, out_coff, res_ld, res_coff, relu;
+  int OT, OH, OW, Nimg;
+  long long M;                  // Nimg*OT*OH*OW
+  int bw, bh, bt, tiles_w, tiles_h, tiles_t;  // BOX mode
+  int a_bytes;                  // bytes TMA writes for A per stage
+  uint32_t idesc;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c, int w, int h,
+                                                   int d, int n, uint16_t ow, uint16_t oh, uint16_t od) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10};"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"(ow), "h"(oh), "h"(od) : "memory");
+}
+
+// smem matrix descriptor, K-major, swizzled (cute/arch/mma_sm100_desc.hpp bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 | [46,48) version=1 |
+// [49,52) base offset | [61,64) layout (2 = 128B, 4 = 64B, 6 = 32B swizzle)
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  constexpr uint32_t row_bytes = BK * 2;
+  constexpr uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  constexpr uint64_t sbo = (8 * row_bytes) >> 4;  // 8-row core-matrix group pitch
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (sbo << 32) | (1ULL << 46) | (layout << 61);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---- the kernel -----------------------------------------------------------------------------
+template <int BK>
+__global__ void __launch_bounds__(kThreads, 2)
+conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvGeom g,
+                 const float* __restrict__ scale, const float* __restrict__ shift, const __half* __restrict__ residual,
+                 __half* __restrict__ y) {
+  constexpr int kABytes = kBM * BK * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [A stages][B stages][barriers][tmem ptr][scale/shift]
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = g.BN * BK * 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kABytes;
+  uint64_t* full_bar = (uint64_t*)(sB + kStages * b_bytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_ptr_s = (uint32_t*)(tmem_full_bar + 1);
+  float* s_scale = (float*)(tmem_ptr_s + 2);
+  float* s_shift = s_scale + kMaxBN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x / g.n_tiles, n_tile = blockIdx.x - m_tile * g.n_tiles;
+  const int n0 = n_tile * g.BN;
+  const int num_kb = g.taps * g.kblocks_per_tap;
+
+  // tile origin
+  long long m0 = (long long)m_tile * kBM;
+  int bn = 0, bt0 = 0, bh0 = 0, bw0 = 0;  // BOX origin
+  if (g.mode == A_BOX) {
+    int r = m_tile;
+    bw0 = (r % g.tiles_w) * g.bw; r /= g.tiles_w;
+    bh0 = (r % g.tiles_h) * g.bh; r /= g.tiles_h;
+    bt0 = (r % g.tiles_t) * g.bt; bn = r / g.tiles_t;
+  }
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  // TMEM columns: power of two >= 32 covering BN
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)g.BN) ncols <<= 1;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {  // stage the per-channel epilogue constants
+    for (int i = threadIdx.x - 64; i < g.BN; i += 128) {
+      int c = n0 + i;
+      s_scale[i] = (scale && c < g.Cout) ? scale[c] : 1.0f;
+      s_shift[i] = (shift && c < g.Cout) ? shift[c] : 0.0f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      // IM2COL start coordinates: output pixel m0 -> (w,h,t,n) + lower corner (= -pad)
+      int iw = 0, ih = 0, it = 0, in_ = 0;
+      if (g.mode == A_IM2COL) {
+        long long r = m0;
+        iw = (int)(r % g.OW); r /= g.OW;
+        ih = (int)(r % g.OH); r /= g.OH;
+        it = (int)(r % g.OT); in_ = (int)(r / g.OT);
+        iw -= g.PW; ih -= g.PH; it -= g.PT;
+      }
+      const uint32_t tx_bytes = (uint32_t)(g.a_bytes + b_bytes);
+      int stage = 0; uint32_t phase = 0;
+      for (int tap = 0; tap < g.taps; ++tap) {
+        const int kw = tap % g.KW, kh = (tap / g.KW) % g.KH, kt = tap / (g.KW * g.KH);
+        for (int kc = 0; kc < g.kblocks_per_tap; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          void* a_dst = sA + stage * kABytes;
+          void* b_dst = sB + stage * b_bytes;
+          const int c0 = kc * BK;
+          if (g.mode == A_LINEAR) {
+            tma_load_2d(&map_a, &full_bar[stage], a_dst, c0, (int)m0);
+          } else if (g.mode == A_BOX) {
+            tma_load_5d(&map_a, &full_bar[stage], a_dst, c0, bw0 + kw - g.PW, bh0 + kh - g.PH, bt0 + kt - g.PT, bn);
+          } else {
+            tma_load_im2col_5d(&map_a, &full_bar[stage], a_dst, c0, iw, ih, it, in_, (uint16_t)kw, (uint16_t)kh, (uint16_t)kt);
+          }
+          tma_load_3d(&map_b, &full_bar[stage], b_dst, c0, tap, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(sA + stage * kABytes), b_addr = smem_u32(sB + stage * b_bytes);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the swizzle atom
+          umma_f16(tmem_base, make_smem_desc<BK>(a_addr + k * 32), make_smem_desc<BK>(b_addr + k * 32), g.idesc,
+                   (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);                   // frees the smem stage when the MMAs retire
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int lane_grp = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = lane_grp * 32 + lane;
+    // output pixel of this row
+    long long pix = -1;
+    if (g.mode == A_BOX) {
+      int dw = row % g.bw, r = row / g.bw;
+      int dh = r % g.bh, dt = r / g.bh;
+      int ow = bw0 + dw, oh = bh0 + dh, ot = bt0 + dt;
+      if (dt < g.bt && ow < g.OW && oh < g.OH && ot < g.OT) pix = (((long long)bn * g.OT + ot) * g.OH + oh) * g.OW + ow;
+    } else {
+      long long m = m0 + row;
+      if (m < g.M) pix = m;
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+    __half* yrow = y + (pix < 0 ? 0 : (size_t)pix * g.out_ld + g.out_coff + n0);
+    const __half* rrow = residual ? residual + (pix < 0 ? 0 : (size_t)pix * g.res_ld + g.res_coff + n0) : nullptr;
+    for (int c = 0; c < g.BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + c, v);
+      tmem_ld_wait();
+      if (pix >= 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // two 8-channel (16-byte) halves
+          const int cc = c + h * 8;
+          if (n0 + cc < g.Cout) {
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[h * 8 + k]), s_scale[cc + k], s_shift[cc + k]);
+            if (rrow) {
+              float rv[8];
+              load16(rrow + cc, rv);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] += rv[k];
+            }
+            if (g.relu) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+            }
+            store16(yrow + cc, f);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+// debug: load one A tile (tap kt,kh,kw, channel block c0) for m_tile and dump the raw stage bytes
+template <int BK>
+__global__ void __launch_bounds__(32) tma_dump_kernel(const __grid_constant__ CUtensorMap map_a, ConvGeom g, int m_tile,
+                                                      int kt, int kh, int kw, int c0, uint8_t* __restrict__ out) {
+  constexpr int kABytes = kBM * BK * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  for (int i = threadIdx.x; i < kABytes / 4; i += 32) ((uint32_t*)smem)[i] = 0xFFFFFFFFu;  // "never written"
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  fence_proxy_async();
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    long long m0 = (long long)m_tile * kBM;
+    mbar_expect_tx(&bar, (uint32_t)g.a_bytes);
+    if (g.mode == A_LINEAR) {
+      tma_load_2d(&map_a, &bar, smem, c0, (int)m0);
+    } else if (g.mode == A_BOX) {
+      int r = m_tile;
+      int bw0 = (r % g.tiles_w) * g.bw; r /= g.tiles_w;
+      int bh0 = (r % g.tiles_h) * g.bh; r /= g.tiles_h;
+      int bt0 = (r % g.tiles_t) * g.bt; int bn = r / g.tiles_t;
+      tma_load_5d(&map_a, &bar, smem, c0, bw0 + kw - g.PW, bh0 + kh - g.PH, bt0 + kt - g.PT, bn);
+    } else {
+      long long r = m0;
+      int iw = (int)(r % g.OW); r /= g.OW;
+      int ih = (int)(r % g.OH); r /= g.OH;
+      int it = (int)(r % g.OT); int in_ = (int)(r / g.OT);
+      tma_load_im2col_5d(&map_a, &bar, smem, c0, iw - g.PW, ih - g.PH, it - g.PT, in_, (uint16_t)kw, (uint16_t)kh, (uint16_t)kt);
+    }
+  }
+  mbar_wait(&bar, 0);
+  __syncwarp();
+  for (int i = threadIdx.x; i < kABytes / 4; i += 32) ((uint32_t*)out)[i] = ((uint32_t*)smem)[i];
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+
+static int load_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col) return 0;
+  cudaDriverEntryPointQueryResult q;
+  void* f = nullptr;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q);
+  if (e != cudaSuccess || !f) return fail(STEP_E_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  g_encode_tiled = (EncodeTiledFn)f;
+  f = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q);
+  if (e != cudaSuccess || !f) return fail(STEP_E_DRIVER, "cuTensorMapEncodeIm2col entry point unavailable");
+  g_encode_im2col = (EncodeIm2colFn)f;
+  return 0;
+}
+
+static CUtensorMapSwizzle swizzle_for(int BK) {
+  return BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+static int pick_bk(int Cin) {
+  int best = 64; long best_cost = -1;
+  const int cands[3] = {64, 32, 16};
+  for (int i = 0; i < 3; ++i) {
+    int bk = cands[i];
+    long cost = (long)((Cin + bk - 1) / bk) * (bk + 16);
+    if (best_cost < 0 || cost < best_cost) { best = bk; best_cost = cost; }
+  }
+  return best;
+}
+
+static void pick_box(int OW, int OH, int OT, int* bw, int* bh, int* bt) {
+  double best = -1;
+  for (int w = 1; w <= OW && w <= kBM; ++w)
+    for (int h = 1; h <= OH && w * h <= kBM; ++h) {
+      int t = kBM / (w * h);
+      if (t > OT) t = OT;
+      if (t < 1) continue;
+      double eff = ((double)OW / (((OW + w - 1) / w) * w)) * ((double)OH / (((OH + h - 1) / h) * h)) *
+                   ((double)OT / (((OT + t - 1) / t) * t)) * ((double)(w * h * t) / kBM);
+      if (eff > best + 1e-9) { best = eff; *bw = w; *bh = h; *bt = t; }
+    }
+}
+
+struct ConvPlan {
+  CUtensorMap map_a, map_b;
+  ConvGeom g;
+  int BK;
+  size_t smem_bytes;
+  dim3 grid;
+};
+
+static int build_plan(const step_conv_params* p, ConvPlan* pl) {
+  if (int rc = load_driver_entry_points()) return rc;
+  STEP_CHECK_ARG(p->ST == 1 && p->SH == 1 && p->SW == 1, "conv3d(f16): stride must be 1 (use the s2d stem)");
+  STEP_CHECK_ARG(p->Cin % 8 == 0 && p->in_ld % 8 == 0 && p->w_ld % 8 == 0 && p->w_ld >= p->Cin,
+                 "conv3d(f16): Cin=%d in_ld=%d w_ld=%d must be multiples of 8", p->Cin, p->in_ld, p->w_ld);
+  STEP_CHECK_ARG(p->Cout % 8 == 0 && p->out_ld % 8 == 0 && p->out_coff % 8 == 0, "conv3d(f16): Cout/out_ld/out_coff %% 8");
+  STEP_CHECK_ARG(!p->residual || (p->res_ld % 8 == 0 && p->res_coff % 8 == 0), "conv3d(f16): res_ld/res_coff %% 8");
+  STEP_CHECK_ARG((((uintptr_t)p->x | (uintptr_t)p->w | (uintptr_t)p->y | (uintptr_t)p->residual) & 15) == 0,
+                 "conv3d(f16): pointers must be 16-byte aligned");
+  ConvGeom& g = pl->g;
+  memset(&g, 0, sizeof(g));
+  const int taps = p->KT * p->KH * p->KW;
+  const bool is_1x1 = taps == 1 && p->PT == 0 && p->PH == 0 && p->PW == 0 && p->OT == p->T && p->OH == p->H && p->OW == p->W;
+  int mode = p->a_mode;
+  if (mode == 0) mode = is_1x1 ? A_LINEAR : A_BOX;
+  STEP_CHECK_ARG(mode == A_LINEAR || mode == A_BOX || mode == A_IM2COL, "conv3d(f16): bad a_mode %d", p->a_mode);
+  STEP_CHECK_ARG(mode != A_LINEAR || is_1x1, "conv3d(f16): LINEAR mode needs a 1x1x1 unpadded filter");
+  g.mode = mode;
+  g.taps = taps; g.KT = p->KT; g.KH = p->KH; g.KW = p->KW; g.PT = p->PT; g.PH = p->PH; g.PW = p->PW;
+  pl->BK = pick_bk(p->Cin);
+  const int BK = pl->BK;
+  g.kblocks_per_tap = (p->Cin + BK - 1) / BK;
+  g.n_tiles = (p->Cout + kMaxBN - 1) / kMaxBN;
+  g.BN = (((p->Cout + g.n_tiles - 1) / g.n_tiles) + 15) / 16 * 16;
+  g.Cout = p->Cout; g.out_ld = p->out_ld; g.out_coff = p->out_coff; g.res_ld = p->res_ld; g.res_coff = p->res_coff;
+  g.relu = p->relu;
+  g.OT = p->OT; g.OH = p->OH; g.OW = p->OW; g.Nimg = p->N;
+  g.M = (long long)p->N * p->OT * p->OH * p->OW;
+  g.idesc = (1u << 4) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);  // f16 x f16 -> f32, K-major A/B
+  long long m_tiles;
+  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult cr;
+  if (mode == A_LINEAR) {
+    STEP_CHECK_ARG(g.M < (1LL << 31), "conv3d(f16): M too large");
+    cuuint64_t dims[2] = {(cuuint64_t)p->Cin, (cuuint64_t)g.M};
+    cuuint64_t strides[1] = {(cuuint64_t)p->in_ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)kBM};
+    cr = g_encode_tiled(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)p->x, dims, strides, box, ones,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    m_tiles = (g.M + kBM - 1) / kBM;
+    g.a_bytes = kBM * BK * 2;
+  } else {
+    cuuint64_t dims[5] = {(cuuint64_t)p->Cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->T, (cuuint64_t)p->N};
+    cuuint64_t strides[4] = {(cuuint64_t)p->in_ld * 2, (cuuint64_t)p->W * p->in_ld * 2,
+                             (cuuint64_t)p->H * p->W * p->in_ld * 2, (cuuint64_t)p->T * p->H * p->W * p->in_ld * 2};
+    if (mode == A_BOX) {
+      pick_box(p->OW, p->OH, p->OT, &g.bw, &g.bh, &g.bt);
+      g.tiles_w = (p->OW + g.bw - 1) / g.bw; g.tiles_h = (p->OH + g.bh - 1) / g.bh; g.tiles_t = (p->OT + g.bt - 1) / g.bt;
+      cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bt, 1};
+      cr = g_encode_tiled(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)p->x, dims, strides, box, ones,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      m_tiles = (long long)p->N * g.tiles_t * g.tiles_h * g.tiles_w;
+      g.a_bytes = g.bw * g.bh * g.bt * BK * 2;
+    } else {
+      // TMA im2col: bounding box lower corner = -pad_low, upper corner = pad_high - (k-1)  (fprop, dilation 1);
+      // rank-5 corners must lie in [-16, 15]
+      const int ph_t = p->OT - p->T + p->KT - 1 - p->PT, ph_h = p->OH - p->H + p->KH - 1 - p->PH,
+                ph_w = p->OW - p->W + p->KW - 1 - p->PW;
+      int lower[3] = {-p->PW, -p->PH, -p->PT};
+      int upper[3] = {ph_w - (p->KW - 1), ph_h - (p->KH - 1), ph_t - (p->KT - 1)};
+      for (int i = 0; i < 3; ++i)
+        STEP_CHECK_ARG(lower[i] >= -16 && lower[i] <= 15 && upper[i] >= -16 && upper[i] <= 15, "conv3d(f16): im2col corner range");
+      cr = g_encode_im2col(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)p->x, dims, strides, lower, upper,
+                           (cuuint32_t)BK, (cuuint32_t)kBM, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK),
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      // Same work-around CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): drivers <= 13.1 set a
+      // descriptor bit that breaks im2col loads from tensors smaller than 128 KiB.
+      int drv = 0;
+      cudaDriverGetVersion(&drv);
+      if (cr == CUDA_SUCCESS && drv <= 13010 &&
+          (size_t)p->N * p->T * p->H * p->W * p->in_ld * 2 < 131072)
+        reinterpret_cast<uint64_t*>(&pl->map_a)[1] &= ~(1ULL << 21);
+      m_tiles = (g.M + kBM - 1) / kBM;
+      g.a_bytes = kBM * BK * 2;
+    }
+  }
+  if (cr != CUDA_SUCCESS) return fail(STEP_E_DRIVER, "conv3d(f16): tensor map (A, mode %d) encode failed: CUresult %d", mode, (int)cr);
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)p->Cin, (cuuint64_t)taps, (cuuint64_t)p->Cout};
+    cuuint64_t strides[2] = {(cuuint64_t)p->w_ld * 2, (cuuint64_t)taps * p->w_ld * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, 1, (cuuint32_t)g.BN};
+    cr = g_encode_tiled(&pl->map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)p->w, dims, strides, box, ones,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(STEP_E_DRIVER, "conv3d(f16): tensor map (B) encode failed: CUresult %d", (int)cr);
+  }
+  STEP_CHECK_ARG(m_tiles * g.n_tiles < (1LL << 31), "conv3d(f16): grid too large");
+  pl->grid = dim3((unsigned)(m_tiles * g.n_tiles));
+  pl->smem_bytes = 1024 + (size_t)kStages * (kBM * BK * 2 + g.BN * BK * 2) + (2 * kStages + 1) * 8 + 8 + 2 * kMaxBN * 4;
+  return 0;
+}
+
+template <int BK>
+static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    if (e != cudaSuccess) return fail((int)e, "conv3d(f16): smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  conv_umma_kernel<BK><<<pl.grid, kThreads, pl.smem_bytes, s>>>(pl.map_a, pl.map_b, pl.g, p->scale, p->shift,
+                                                               (const __half*)p->residual, (__half*)p->y);
+  STEP_LAUNCH_CHECK("conv_umma_kernel");
+  return 0;
+}
+
+int conv3d_umma_launch(const step_conv_params* p, step_stream_t stream) {
+  ConvPlan pl;
+  if (int rc = build_plan(p, &pl)) return rc;
+  if (pl.BK == 64) return launch_bk<64>(pl, p, cu(stream));
+  if (pl.BK == 32) return launch_bk<32>(pl, p, cu(stream));
+  return launch_bk<16>(pl, p, cu(stream));
+}
+
+}  // namespace step
+
+using namespace step;
+
+// Test hook (tests/test_conv_umma.py): raw bytes of one staged A tile -> out [128 * BK * 2].
+extern "C" int step_debug_tma_tile(const step_conv_params* p, int m_tile, int kt, int kh, int kw, int c0, void* out,
+                                   int* bk_out, int* box_out /*[3]*/, step_stream_t stream) {
+  ConvPlan pl;
+  if (int rc = build_plan(p, &pl)) return rc;
+  if (bk_out) *bk_out = pl.BK;
+  if (box_out) { box_out[0] = pl.g.bw; box_out[1] = pl.g.bh; box_out[2] = pl.g.bt; }
+  size_t smem = 1024 + (size_t)kBM * pl.BK * 2;
+  if (pl.BK == 64) tma_dump_kernel<64><<<1, 32, smem, cu(stream)>>>(pl.map_a, pl.g, m_tile, kt, kh, kw, c0, (uint8_t*)out);
+  else if (pl.BK == 32) tma_dump_kernel<32><<<1, 32, smem, cu(stream)>>>(pl.map_a, pl.g, m_tile, kt, kh, kw, c0, (uint8_t*)out);
+  else tma_dump_kernel<16><<<1, 32, smem, cu(stream)>>>(pl.map_a, pl.g, m_tile, kt, kh, kw, c0, (uint8_t*)out);
+  STEP_LAUNCH_CHECK("tma_dump_kernel");
+  return 0;
+}

@@ -1,0 +1,316 @@
+"""`TwoBranchNet` and `ContextNet` with the reference's constructor / forward signatures and
+state_dict keys (models/two_branch.py:113-373), running on libstep_b200.so.
+
+TwoBranchNet.forward(global_feat[R,T',832,7,7], context_feat=None|[R,1024,T',1,1], tubes, targets)
+  -> (global_prob[R,cls], local_loc[R,T',4], first_loc[R,T,4], last_loc[R,T,4], loss x3)
+Inference only (targets must be None): the three losses are returned as zeros exactly as the
+reference does when targets is None (two_branch.py:278-280, 338-340).
+
+Layout tricks (none changes results beyond fp rounding):
+  * ROI features and the 1x1x1 `downsample` output share one [R*T',7,7,1088] buffer, so the concat
+    of two_branch.py:256 is free;
+  * the classifier is linear, so the temporal mean (two_branch.py:249) is taken on the features
+    before `global_cls` instead of on the logits (T' times less work);
+  * Linear / global_cls weights are permuted once from the reference's (c*49 + h*7 + w) flattening
+    (two_branch.py:239,261) to channels-last ((h*7 + w)*256 + c).
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import engine as E
+from .engine import Act
+from .i3d import I3D_head
+from .networks import to_act, weights_init
+
+__all__ = ['ContextNet', 'TwoBranchNet']
+
+
+def build_conv(base_name='i3d', kinetics_pretrain=None, mode='global', freeze_affine=True):
+    """two_branch.py:20-57"""
+    if base_name != "i3d":
+        raise NotImplementedError
+    i3d = I3D_head()
+    if kinetics_pretrain is not None:
+        import os
+        if not os.path.isfile(kinetics_pretrain):
+            raise ValueError("Kinetics_pretrain doesn't exist: {}".format(kinetics_pretrain))
+        model_dict = i3d.state_dict()
+        pre = torch.load(kinetics_pretrain, map_location="cpu")
+        model_dict.update({k: v for k, v in pre.items() if k in model_dict})
+        i3d.load_state_dict(model_dict)
+    if mode == 'context':
+        model = nn.Sequential(i3d.maxPool3d, i3d.mixed_5b, i3d.mixed_5c)
+    else:
+        model = nn.Sequential(i3d.mixed_5b, i3d.mixed_5c)
+    if freeze_affine:
+        for m in model.modules():
+            if m.__class__.__name__.find('BatchNorm') != -1:
+                for p in m.parameters():
+                    p.requires_grad = False
+    return model
+
+
+def _packed(mod, code, kind="conv"):
+    """Pack (and cache on the module) the weights of an nn.Conv2d / nn.Conv3d / nn.Linear container."""
+    key = (code, kind) + E.params_key(mod.weight, mod.bias)
+    c = mod.__dict__.get("_step_cache")
+    if c is None or c[0] != key:
+        if kind == "conv":
+            w = E.pack_conv_weight(mod.weight, code)
+            bias = mod.bias.detach().float().contiguous() if mod.bias is not None else None
+            val = (w, bias)
+        else:
+            raise AssertionError(kind)
+        mod.__dict__["_step_cache"] = (key, val)
+        c = mod.__dict__["_step_cache"]
+    return c[1]
+
+
+def _perm_flat(w2d, fc, ps):
+    """[n, fc*ps*ps] with column c*ps*ps + p  ->  column p*fc + c."""
+    n = w2d.shape[0]
+    return w2d.detach().float().view(n, fc, ps * ps).permute(0, 2, 1).reshape(n, fc * ps * ps).contiguous()
+
+
+def conv2d(mod, x, relu, residual=None, out=None):
+    """nn.Conv2d container (kernel 1 or 3, stride 1, pad k//2) on frames Act [F,1,H,W,*]."""
+    w, bias = _packed(mod, x.code)
+    kh, kw = mod.kernel_size
+    if out is None:
+        out = Act.empty(x.N, 1, x.H, x.W, mod.out_channels, x.code, x.device)
+    return E.conv(x, w, None, bias, out, (1, kh, kw), (1, 1, 1), (0, kh // 2, kw // 2), relu, residual)
+
+
+class Bottleneck(nn.Module):
+    """two_branch.py:60-84"""
+
+    def __init__(self, inplanes, planes, stride=1):
+        super(Bottleneck, self).__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=1, bias=False)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.conv3 = nn.Conv2d(planes, inplanes, kernel_size=1, bias=False)
+        self.relu = nn.ReLU(inplace=True)
+        self.stride = stride
+
+    def forward(self, x):
+        o = conv2d(self.conv1, x, True)
+        o = conv2d(self.conv2, o, True)
+        return conv2d(self.conv3, o, True, residual=x)  # out += residual; relu  (two_branch.py:79-82)
+
+
+class Bottleneck_resample(nn.Module):
+    """two_branch.py:86-111"""
+
+    def __init__(self, inplanes, outplanes, planes, stride=1):
+        super(Bottleneck_resample, self).__init__()
+        self.conv1 = nn.Conv2d(inplanes, outplanes, kernel_size=1, bias=False)
+        self.conv2 = nn.Conv2d(inplanes, planes, kernel_size=1, bias=False)
+        self.conv3 = nn.Conv2d(planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.conv4 = nn.Conv2d(planes, outplanes, kernel_size=1, bias=False)
+        self.relu = nn.ReLU(inplace=True)
+        self.stride = stride
+
+    def forward(self, x):
+        res = conv2d(self.conv1, x, False)
+        o = conv2d(self.conv2, x, True)
+        o = conv2d(self.conv3, o, True)
+        return conv2d(self.conv4, o, True, residual=res)
+
+
+class ContextNet(nn.Module):
+    """two_branch.py:113-161.  forward(conv_feat[N,T',832,H',W']) -> [N,1024,T',1,1].
+
+    The reference hard-codes AvgPool3d((1,13,13)) and therefore only accepts 400x400 inputs
+    (25 -> 13 after the pool); here the average is taken over the whole map, which is the same
+    number at 400x400 and well defined elsewhere."""
+
+    def __init__(self, cfg):
+        super(ContextNet, self).__init__()
+        self.T = cfg.T
+        self.freeze_stats = cfg.freeze_stats
+        self.freeze_affine = cfg.freeze_affine
+        self.fp16 = cfg.fp16
+        self.i3d_conv_context = build_conv(cfg.base_net, cfg.kinetics_pretrain, 'context', self.freeze_affine)
+        self.avg_pool = nn.AvgPool3d((1, 13, 13), (1, 1, 1))  # kept for repr / state parity; not called
+        self._init_net()
+
+    def forward(self, conv_feat):
+        ctx = self.forward_act(to_act(conv_feat, E.dtype_code(self.fp16)))  # [N, T', 1024] fp32
+        return ctx.permute(0, 2, 1).unsqueeze(-1).unsqueeze(-1)
+
+    def forward_act(self, a):
+        """Act [N,T',H',W',832] -> fp32 tensor [N, T', 1024] (spatial mean)."""
+        x = self.i3d_conv_context[0](a)
+        x = self.i3d_conv_context[1](x)
+        x = self.i3d_conv_context[2](x)
+        # mean over the H*W pixels of every (n, t): [A = N*T', B = H*W, P = 1, C]
+        y = E.mean_mid(x.data_ptr(), x.code, x.N * x.T, x.H * x.W, 1, x.C, x.ld, x.device)
+        return y.view(x.N, x.T, x.C)
+
+    def _init_net(self):
+        pass
+
+    def set_device(self, device):
+        self.device = device
+
+    def train(self, mode=True):
+        nn.Module.train(self, mode)
+        return self
+
+
+class TwoBranchNet(nn.Module):
+    """two_branch.py:164-373"""
+
+    def __init__(self, cfg, cls_only=False):
+        super(TwoBranchNet, self).__init__()
+        self.num_classes = cfg.num_classes
+        self.T = cfg.T
+        self.base_net = cfg.base_net
+        self.freeze_stats = cfg.freeze_stats
+        self.freeze_affine = cfg.freeze_affine
+        self.fc_dim = cfg.fc_dim
+        self.dropout_prob = cfg.dropout
+        self.pool_size = cfg.pool_size
+        self.no_context = cfg.no_context
+        self.fp16 = cfg.fp16
+        self.cls_only = cls_only
+
+        self.i3d_conv = build_conv(cfg.base_net, cfg.kinetics_pretrain, 'global', self.freeze_affine)
+        self.downsample = nn.Conv3d(1024, self.fc_dim, kernel_size=1, stride=1, bias=True)
+        self.dropout = nn.Dropout(self.dropout_prob)
+        self.global_cls = nn.Conv3d(self.fc_dim * self.pool_size ** 2 + (1024 if not self.no_context else 0),
+                                    self.num_classes, (1, 1, 1), bias=True)
+        if not self.cls_only:
+            self.local_conv = nn.Sequential(Bottleneck_resample(832 + self.fc_dim, 1024, 256),
+                                            Bottleneck(1024, 256), Bottleneck(1024, 256))
+            self.downsample2 = nn.Conv2d(1024, self.fc_dim, kernel_size=1, stride=1, bias=True)
+            self.local_reg = nn.Linear(self.fc_dim * self.pool_size ** 2, 4)
+            self.neighbor_reg1 = nn.Linear(self.fc_dim * self.pool_size ** 2, 4)  # for tube t-1
+            self.neighbor_reg2 = nn.Linear(self.fc_dim * self.pool_size ** 2, 4)  # for tube t+1
+        self.device = None
+        self._init_net()
+
+    # ---- weights ------------------------------------------------------------------------------
+    def _head_weights(self):
+        """fp32 permuted copies of global_cls / local_reg / neighbor_reg (cached per version)."""
+        mods = [self.global_cls] + ([self.local_reg, self.neighbor_reg1, self.neighbor_reg2] if not self.cls_only else [])
+        key = E.params_key(*[t for m in mods for t in (m.weight, m.bias)])
+        c = self.__dict__.get("_hw")
+        if c is None or c[0] != key:
+            D = self.fc_dim * self.pool_size ** 2
+            gw = self.global_cls.weight.detach().float().view(self.num_classes, -1)
+            val = {"cls_w": _perm_flat(gw[:, :D], self.fc_dim, self.pool_size),
+                   "cls_b": self.global_cls.bias.detach().float().contiguous(),
+                   "ctx_w": gw[:, D:].contiguous() if gw.shape[1] > D else None}
+            if not self.cls_only:
+                for name in ("local_reg", "neighbor_reg1", "neighbor_reg2"):
+                    m = getattr(self, name)
+                    val[name + "_w32"] = _perm_flat(m.weight, self.fc_dim, self.pool_size)
+                    val[name + "_b"] = m.bias.detach().float().contiguous()
+            self.__dict__["_hw"] = (key, val)
+            c = self.__dict__["_hw"]
+        return c[1]
+
+    def _reg_weight(self, name, code):
+        hw = self._head_weights()
+        k = name + ("_w16" if code == L.F16 else "_w32")
+        if k not in hw:
+            hw[k] = hw[name + "_w32"].to(torch.float16).contiguous()
+        return hw[k], hw[name + "_b"]
+
+    # ---- forward ------------------------------------------------------------------------------
+    def forward(self, global_feat, context_feat=None, tubes=None, targets=None):
+        if targets is not None:
+            raise NotImplementedError("step_b200.TwoBranchNet: training losses (two_branch.py:276-333) are the "
+                                      "'next' row of SURVEY.md section 8f; inference only")
+        dev = self.device
+        if dev is not None and str(dev) != "cpu":
+            global_feat = global_feat.to(dev)
+            if context_feat is not None:
+                context_feat = context_feat.to(dev)
+        L.need_cuda(global_feat)
+        code = E.dtype_code(self.fp16)
+        N, T, C, W, H = global_feat.shape
+        # stage [ROI features | downsample output] in one [N*T,7,7,1088] buffer (two_branch.py:256)
+        cat = Act.empty(N, T, W, H, C + self.fc_dim, code, global_feat.device)
+        src = to_act(global_feat, code)
+        cat.buf[..., :C].copy_(src.buf[..., src.coff:src.coff + C])
+        ctx_mean = None
+        if context_feat is not None:
+            L.need_cuda(context_feat)
+            cf = context_feat.detach().float().contiguous().view(N * context_feat.shape[1], T)
+            # mean over T' of [N*1024, T', 1] -> [N, 1024]
+            ctx_mean = E.mean_mid(cf.data_ptr(), L.F32, N * context_feat.shape[1], T, 1, 1, 1, cf.device).view(N, -1)
+        prob, loc, first, last = self.forward_act(cat, ctx_mean, None)
+        z = torch.tensor(0., device=prob.device)
+        return prob, loc, first, last, z.view(-1), z.view(-1), z.view(-1)
+
+    def forward_act(self, cat, ctx_mean=None, ctx_row_map=None):
+        """cat: Act [R, T', 7, 7, ld >= 832 + fc] whose first 832 channels hold the ROI features.
+        ctx_mean: fp32 [rows, 1024] temporal mean of the context feature; ctx_row_map: int32 [R]
+        row of ctx_mean for each tube (None = identity).  Returns fp32 tensors."""
+        R, T, ps = cat.N, cat.T, self.pool_size
+        code = cat.code
+        roi = cat.slice(0, 832)
+        g = self.i3d_conv[0](roi)
+        g = self.i3d_conv[1](g)
+        # downsample: 1x1x1, bias, no activation (two_branch.py:236) -> channels [832, 832+fc) of cat
+        w, bias = _packed(self.downsample, code)
+        gconv = cat.slice(832, self.fc_dim)
+        E.conv(g, w, None, bias, gconv, (1, 1, 1), relu=False)
+        hw = self._head_weights()
+        D = self.fc_dim * ps * ps
+        # temporal mean then classifier (+ context columns) then sigmoid (two_branch.py:246-249,337)
+        xbar = E.mean_mid(gconv.data_ptr(), code, R, T, ps * ps, self.fc_dim, cat.ld, cat.device)
+        has_ctx = ctx_mean is not None and hw["ctx_w"] is not None
+        logits = E.linear_small_n(xbar, R, D, D, hw["cls_w"], hw["cls_b"], self.num_classes,
+                                  act=0 if has_ctx else 1)
+        if has_ctx:
+            E.linear_small_n(ctx_mean, R, 1024, 1024, hw["ctx_w"], None, self.num_classes, y=logits, act=1,
+                             accumulate=True, row_map=ctx_row_map)
+        prob = logits
+        if self.cls_only:
+            z = torch.tensor([0.], device=prob.device)
+            return prob, z, z, z
+        # local branch on frames (two_branch.py:253-262)
+        lf = self.local_conv(cat.frames())
+        w2, b2 = _packed(self.downsample2, code)
+        lf2 = Act.empty(R * T, 1, ps, ps, self.fc_dim, code, cat.device)
+        E.conv(lf, w2, None, b2, lf2, (1, 1, 1), relu=False)
+        wr, br = self._reg_weight("local_reg", code)
+        local_loc = E.linear_small_n(lf2.buf, R * T, D, D, wr, br, 4).view(R, T, 4)
+        # neighbour regressors on the first / last chunk (two_branch.py:265-270)
+        Tc = self.T
+        chunks = int(T / Tc)
+        half = int(Tc / 2)
+        s0, s1 = max(int(Tc / 2) - half, 0), min(int(Tc / 2) + half + 1, T)
+        e0 = max((chunks - 1) * Tc + int(Tc / 2) - half, 0)
+        e1 = min((chunks - 1) * Tc + int(Tc / 2) + half + 1, T)
+        first = local_loc[:, s0:s1].contiguous()
+        last = local_loc[:, e0:e1].contiguous()
+        base = torch.arange(R, device=cat.device, dtype=torch.int32).view(R, 1) * T
+        rows_f = (base + torch.arange(s0, s1, device=cat.device, dtype=torch.int32).view(1, -1)).reshape(-1).contiguous()
+        rows_l = (base + torch.arange(e0, e1, device=cat.device, dtype=torch.int32).view(1, -1)).reshape(-1).contiguous()
+        w1, b1 = self._reg_weight("neighbor_reg1", code)
+        w2n, b2n = self._reg_weight("neighbor_reg2", code)
+        E.linear_small_n(lf2.buf, rows_f.numel(), D, D, w1, b1, 4, y=first.view(-1, 4), accumulate=True, row_map=rows_f)
+        E.linear_small_n(lf2.buf, rows_l.numel(), D, D, w2n, b2n, 4, y=last.view(-1, 4), accumulate=True, row_map=rows_l)
+        return prob, local_loc, first, last
+
+    def _init_net(self):
+        self.global_cls.apply(weights_init)
+        self.downsample.apply(weights_init)
+        if not self.cls_only:
+            self.local_conv.apply(weights_init)
+            self.local_reg.apply(weights_init)
+            self.downsample2.apply(weights_init)
+            self.neighbor_reg1.apply(weights_init)
+            self.neighbor_reg2.apply(weights_init)
+
+    def set_device(self, device):
+        self.device = device
+
+    def train(self, mode=True):
+        nn.Module.train(self, mode)
+        return self

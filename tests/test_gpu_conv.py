@@ -1,0 +1,228 @@
+"""GPU: the convolution kernels.
+  * SIMT fp32 (parity mode) vs torch-CPU conv3d (the reference's arithmetic, i3dpt.py:103-111);
+  * TMA addressing (box / im2col) checked byte-for-byte through the debug tile dump;
+  * tcgen05 fp16 kernel vs the SIMT kernel on identical fp16 inputs (fp32 accumulate both:
+    differences are accumulation order only -> tolerance 2e-3 of max|ref| + 1 fp16 ulp).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from step_b200 import _lib as L
+from step_b200 import engine as E
+from step_b200.engine import Act
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_conv(x_ndhwc, w, k, stride, scale, shift, relu, residual):
+    """torch-CPU fp32 reference: TF-SAME padded conv3d + affine + residual + relu, NDHWC in/out."""
+    x = x_ndhwc.permute(0, 4, 1, 2, 3).float().cpu()
+    pads = [E.same_pad(k[i], stride[i]) for i in range(3)]
+    x = F.pad(x, (pads[2][0], pads[2][1], pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
+    y = F.conv3d(x, w.float().cpu(), stride=stride)
+    if scale is not None:
+        y = y * scale.cpu().view(1, -1, 1, 1, 1)
+    if shift is not None:
+        y = y + shift.cpu().view(1, -1, 1, 1, 1)
+    y = y.permute(0, 2, 3, 4, 1)
+    if residual is not None:
+        y = y + residual.float().cpu()
+    return F.relu(y) if relu else y
+
+
+def run_conv(x, w, code, k, stride, scale, shift, relu, residual, a_mode, coff=0, extra=0):
+    Cout = w.shape[0]
+    wp = E.pack_conv_weight(w.cuda(), code)
+    xa = Act(x.contiguous())
+    od = tuple(-(-d // s) for d, s in zip((xa.T, xa.H, xa.W), stride))
+    buf = torch.zeros((xa.N,) + od + (Cout + coff + extra,), dtype=E.torch_dtype(code), device="cuda")
+    out = Act(buf, Cout, coff)
+    res = Act(residual.contiguous()) if residual is not None else None
+    E.conv(xa, wp, scale, shift, out, k, stride, None, relu, res, a_mode=a_mode)
+    torch.cuda.synchronize()
+    return buf
+
+
+CASES_F32 = [
+    # N, T, H, W, Cin, Cout, k, stride
+    (2, 4, 9, 7, 8, 24, (1, 1, 1), (1, 1, 1)),
+    (1, 5, 9, 11, 12, 20, (3, 3, 3), (1, 1, 1)),
+    (1, 8, 20, 18, 4, 16, (7, 7, 7), (2, 2, 2)),
+    (3, 1, 7, 7, 16, 8, (1, 3, 3), (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", CASES_F32)
+def test_simt_fp32_matches_torch_cpu(case):
+    N, T, H, W, Cin, Cout, k, stride = case
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, T, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, *k, generator=g) / (Cin * k[0] * k[1] * k[2]) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g)
+    od = tuple(-(-d // s) for d, s in zip((T, H, W), stride))
+    res = torch.randn((N,) + od + (Cout,), generator=g)
+    y = run_conv(x.cuda(), w, L.F32, k, stride, scale.cuda(), shift.cuda(), True, res.cuda(), L.A_AUTO, coff=8, extra=4)
+    ref = ref_conv(x, w, k, stride, scale, shift, True, res)
+    got = y[..., 8:8 + Cout].cpu()
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
+    assert float(y[..., :8].abs().max()) == 0 and float(y[..., 8 + Cout:].abs().max()) == 0   # slice only
+
+
+# ---- TMA tile dump ---------------------------------------------------------------------------
+def unswizzle(raw_u16, BK):
+    """raw stage bytes (as uint16) -> [128, BK] logical tile, undoing the TMA/UMMA swizzle."""
+    row_bytes = BK * 2
+    tile = np.zeros((128, BK), np.uint16)
+    raw = raw_u16.view(np.uint8)
+    for r in range(128):
+        for ch in range(row_bytes // 16):
+            if row_bytes == 128:
+                pch = ch ^ (r % 8)
+            elif row_bytes == 64:
+                pch = ch ^ ((r >> 1) & 3)
+            else:
+                pch = ch ^ ((r >> 2) & 1)
+            off = r * row_bytes + pch * 16
+            tile[r, ch * 8:(ch + 1) * 8] = raw[off:off + 16].view(np.uint16)
+    return tile
+
+
+def id_tensor(N, T, H, W, C):
+    ids = (np.arange(N * T * H * W * C, dtype=np.int64) % 65521 + 1).astype(np.uint16).reshape(N, T, H, W, C)
+    return ids
+
+
+def conv_params(x, Cin, Cout, k, pad_lo, out_dims, a_mode, w):
+    p = L.ConvParams()
+    p.dtype = L.F16
+    p.N, p.T, p.H, p.W = x.shape[:4]
+    p.Cin, p.in_ld = Cin, x.shape[4]
+    p.Cout, p.out_ld, p.out_coff = Cout, Cout, 0
+    p.KT, p.KH, p.KW = k
+    p.ST = p.SH = p.SW = 1
+    p.PT, p.PH, p.PW = pad_lo
+    p.OT, p.OH, p.OW = out_dims
+    p.w_ld = w.shape[2]
+    p.x, p.w, p.y = x.data_ptr(), w.data_ptr(), x.data_ptr()
+    p.a_mode = a_mode
+    return p
+
+
+@pytest.mark.parametrize("a_mode", [L.A_BOX, L.A_IM2COL])
+@pytest.mark.parametrize("shape", [(2, 3, 5, 6, 64), (1, 4, 14, 14, 32), (2, 8, 7, 7, 16), (1, 2, 9, 10, 96)])
+def test_tma_tile_addressing(a_mode, shape):
+    N, T, H, W, C = shape
+    ids = id_tensor(N, T, H, W, C)
+    x = torch.from_numpy(ids.view(np.int16)).cuda().view(torch.float16)
+    k, pad = (3, 3, 3), (1, 1, 1)
+    w = torch.zeros((16, 27, C), dtype=torch.float16, device="cuda")
+    p = conv_params(x, C, 16, k, pad, (T, H, W), a_mode, w)
+    bk = ctypes.c_int(0)
+    box = (ctypes.c_int * 3)()
+    out = torch.zeros(128 * 64 * 2, dtype=torch.uint8, device="cuda")
+    M = N * T * H * W
+    checked = 0
+    for (kt, kh, kw) in [(0, 0, 0), (1, 1, 1), (2, 2, 2), (0, 2, 1)]:
+        n_tiles = None
+        for m_tile in range(64):
+            L.check(L.lib().step_debug_tma_tile(p, m_tile, kt, kh, kw, 0, L.ptr(out), ctypes.byref(bk), box, L.stream()))
+            torch.cuda.synchronize()
+            BK = bk.value
+            raw = out.cpu().numpy()[:128 * BK * 2].view(np.uint16)
+            tile = unswizzle(raw, BK)
+            bw, bh, bt = box[0], box[1], box[2]
+            if a_mode == L.A_BOX:
+                tw, th, tt = -(-W // bw), -(-H // bh), -(-T // bt)
+                n_tiles = N * tt * th * tw
+                if m_tile >= n_tiles:
+                    break
+                r = m_tile
+                w0 = (r % tw) * bw; r //= tw
+                h0 = (r % th) * bh; r //= th
+                t0 = (r % tt) * bt; n = r // tt
+                rows = [(n, t0 + dt, h0 + dh, w0 + dw) for dt in range(bt) for dh in range(bh) for dw in range(bw)]
+            else:
+                n_tiles = -(-M // 128)
+                if m_tile >= n_tiles:
+                    break
+                rows = []
+                for m in range(m_tile * 128, m_tile * 128 + 128):
+                    if m >= M:
+                        rows.append(None); continue
+                    ww = m % W; hh = (m // W) % H; tt_ = (m // (W * H)) % T; nn = m // (W * H * T)
+                    rows.append((nn, tt_, hh, ww))
+            for ri, pix in enumerate(rows):
+                if pix is None:
+                    continue
+                n, t, h, ww = pix
+                if a_mode == L.A_BOX and (t >= T or h >= H or ww >= W):
+                    continue  # box overhang rows: never stored by the epilogue
+                it, ih, iw = t + kt - 1, h + kh - 1, ww + kw - 1
+                exp = ids[n, it, ih, iw, :BK] if (0 <= it < T and 0 <= ih < H and 0 <= iw < W) else np.zeros(BK, np.uint16)
+                assert np.array_equal(tile[ri], exp), (a_mode, shape, (kt, kh, kw), m_tile, ri, pix)
+                checked += 1
+    assert checked > 100
+
+
+CASES_F16 = [
+    # N, T, H, W, Cin, Cout, k
+    (2, 4, 14, 14, 64, 64, (1, 1, 1)),
+    (1, 3, 9, 11, 192, 96, (1, 1, 1)),
+    (2, 8, 7, 7, 160, 320, (3, 3, 3)),
+    (1, 8, 14, 14, 96, 208, (3, 3, 3)),
+    (1, 4, 12, 12, 16, 48, (3, 3, 3)),
+    (1, 4, 10, 9, 24, 64, (3, 3, 3)),
+    (5, 1, 7, 7, 256, 256, (1, 3, 3)),
+    (1, 2, 28, 28, 32, 32, (3, 3, 3)),
+]
+
+
+@pytest.mark.parametrize("a_mode", [L.A_BOX, L.A_IM2COL])
+@pytest.mark.parametrize("case", CASES_F16)
+def test_umma_fp16_matches_simt(case, a_mode):
+    N, T, H, W, Cin, Cout, k = case
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, T, H, W, Cin, generator=g).half().cuda()
+    w = (torch.randn(Cout, Cin, *k, generator=g) / (Cin * k[0] * k[1] * k[2]) ** 0.5).half()
+    scale = (torch.rand(Cout, generator=g) + 0.5).cuda()
+    shift = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(N, T, H, W, Cout, generator=g).half().cuda()
+    mode = L.A_AUTO if k == (1, 1, 1) else a_mode
+    ref = run_conv(x, w, L.F16, k, (1, 1, 1), scale, shift, True, res, L.A_SIMT, coff=8, extra=8).float()
+    got = run_conv(x, w, L.F16, k, (1, 1, 1), scale, shift, True, res, mode, coff=8, extra=8).float()
+    tol = 2e-3 * float(ref.abs().max()) + 2e-3
+    err = float((got - ref).abs().max())
+    assert err <= tol, "max err %g > %g" % (err, tol)
+    assert float(got[..., :8].abs().max()) == 0 and float(got[..., 8 + Cout:].abs().max()) == 0
+
+
+def test_stem_s2d_fp16_vs_fp32_simt():
+    """the space-to-depth stem (fp16, tcgen05) against the stride-2 fp32 SIMT conv of the same layer."""
+    from step_b200 import synth
+    import step_b200
+    cfg16, cfg32 = synth.make_cfg(fp16=True), synth.make_cfg(fp16=False)
+    sd = synth.base_net_state_dict()
+    x = synth.make_clips(1, 8, 32, 32).cuda()
+    outs = []
+    for cfg in (cfg16, cfg32):
+        net = step_b200.BaseNet(cfg).cuda()
+        net.load_state_dict(sd)
+        stem = net.base_model[0]
+        code = E.dtype_code(cfg.fp16)
+        src = x.contiguous()
+        if code == L.F16:
+            s2d = Act.empty(1, 4, 16, 16, 32, L.F16, x.device)
+            L.check(L.lib().step_clip_to_s2d_f16(L.ptr(src), 1, 8, 3, 32, 32, L.ptr(s2d.buf), 32, L.stream()))
+            outs.append(stem.forward_s2d(s2d).buf.float())
+        else:
+            a = Act.empty(1, 8, 32, 32, 4, L.F32, x.device)
+            L.check(L.lib().step_clip_to_ndhwc(L.ptr(src), 1, 8, 3, 32, 32, L.ptr(a.buf), L.F32, 4, L.stream()))
+            outs.append(stem(a).buf)
+    torch.cuda.synchronize()
+    err = float((outs[0] - outs[1]).abs().max())
+    assert err <= 2e-2 * float(outs[1].abs().max()), err

@@ -1,0 +1,135 @@
+"""GPU: module- and pipeline-level parity against the committed golden vectors (outputs of the
+unmodified reference on seeded synthetic inputs) and the oracle.
+
+Tolerances:
+  fp32 path (cfg.fp16=False, SIMT):  atol = 1e-4 * max|ref|, rtol = 1e-4   (accumulation order only)
+  fp16 path (cfg.fp16=True, tcgen05, fp32 accumulate): max-abs <= 2e-2 * max|ref| at the trunk output,
+      mean-relative <= 1e-2; sigmoid scores <= 5e-3 abs; boxes <= 1.5 px.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tubes as otubes
+from step_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+PIPES = {
+    "pipe_c1": dict(T=2, max_iter=1, NUM_CHUNKS={1: 1}, image_size=(112, 112)),
+    "pipe_spatial": dict(T=4, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 1}, image_size=(112, 112)),
+    "pipe_temporal_predict": dict(T=3, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 3}, temporal_mode="predict", image_size=(112, 112)),
+    "pipe_temporal_extrapolate": dict(T=3, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 3}, temporal_mode="extrapolate", image_size=(112, 112)),
+    "pipe_temporal_mean": dict(T=3, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 3}, temporal_mode="mean", image_size=(112, 112)),
+}
+
+
+def build(cfg, context=False):
+    import step_b200
+    nets = {"base_net": step_b200.BaseNet(cfg), "roi_net": step_b200.ROINet(cfg.pool_mode, cfg.pool_size)}
+    nets["base_net"].load_state_dict(synth.base_net_state_dict(), strict=True)
+    for i in range(cfg.max_iter):
+        h = step_b200.TwoBranchNet(cfg)
+        h.load_state_dict(synth.head_state_dict(100 + i, cfg), strict=True)
+        nets["det_net%d" % i] = h
+    if context:
+        c = step_b200.ContextNet(cfg)
+        c.load_state_dict(synth.context_net_state_dict(), strict=True)
+        nets["context_net"] = c
+    for k in nets:
+        nets[k] = nets[k].cuda().eval()
+        if hasattr(nets[k], "set_device"):
+            nets[k].set_device("cuda:0")
+    return nets
+
+
+def run(name, g, fp16, context=False, **cfg_kw):
+    import step_b200
+    cfg = synth.make_cfg(fp16=fp16, **cfg_kw)
+    nets = build(cfg, context)
+    B, T_in, HW, N = int(g["B"]), int(g["T_in"]), int(g["HW"]), int(g["N"])
+    x = synth.make_clips(B, T_in, HW, HW).cuda()
+    tubes = synth.make_proposals(B, N, cfg.T * cfg.NUM_CHUNKS[1], HW, HW)
+    with torch.no_grad():
+        cf = nets["base_net"](x)
+        ctx = nets["context_net"](cf) if context else None
+        hist, traj = step_b200.inference(cfg, cf, ctx, nets, cfg.max_iter, tubes)
+    torch.cuda.synchronize()
+    return cfg, cf, ctx, hist, traj
+
+
+def check(name, g, cfg, cf, hist, traj, fp16):
+    HW = int(g["HW"])
+    if "conv_feat" in g:
+        ref = g["conv_feat"]
+        got = cf.float().cpu().numpy()
+        assert got.shape == ref.shape
+        mx = np.abs(ref).max()
+        if fp16:
+            assert np.abs(got - ref).max() <= 2e-2 * mx
+            assert np.abs(got - ref).mean() <= 1e-2 * np.abs(ref).mean()
+        else:
+            assert np.allclose(got, ref, rtol=1e-4, atol=1e-4 * mx)
+    p_tol = 5e-3 if fp16 else 2e-5
+    b_tol = 1.5 if fp16 else 2e-3
+    for i, h in enumerate(hist):
+        assert np.abs(h["pred_prob"][:, 0].float().cpu().numpy() - g["prob%d" % i]).max() <= p_tol, (name, i)
+        extends = i + 1 < cfg.max_iter and cfg.NUM_CHUNKS[i + 2] == cfg.NUM_CHUNKS[i + 1] + 2
+        loc = h["pred_loc"].cpu().numpy()
+        v = loc if extends else otubes.valid_tubes(loc, HW, HW)
+        assert np.abs(v - g["loc_valid%d" % i]).max() <= b_tol, (name, i)
+        if "first%d" % i in g and h["pred_first_loc"] is not None:
+            assert np.abs(h["pred_first_loc"].cpu().numpy() - g["first%d" % i]).max() <= b_tol
+            assert np.abs(h["pred_last_loc"].cpu().numpy() - g["last%d" % i]).max() <= b_tol
+        assert list(h["tubes_nums"]) == g["nums%d" % i].tolist()
+        tr = np.concatenate([t[0] for t in traj[i]], 0)
+        assert tr.shape == g["traj%d" % i].shape and np.abs(tr - g["traj%d" % i]).max() <= b_tol, (name, i)
+
+
+@pytest.mark.parametrize("fp16", [False, True], ids=["fp32", "fp16"])
+@pytest.mark.parametrize("name", list(PIPES))
+def test_pipeline_matches_reference_golden(golden, name, fp16):
+    g = golden(name)
+    cfg, cf, ctx, hist, traj = run(name, g, fp16, **PIPES[name])
+    assert tuple(cf.shape) == (int(g["B"]), int(g["T_in"]) // 4, 832, int(g["HW"]) // 16, int(g["HW"]) // 16)
+    check(name, g, cfg, cf, hist, traj, fp16)
+
+
+@pytest.mark.parametrize("fp16", [False, True], ids=["fp32", "fp16"])
+def test_native_ava_shape_with_context(golden, fp16):
+    """36x400x400, N=3, temporal predict, ContextNet on -- the reference's shipped configuration."""
+    g = golden("pipe_ava_context")
+    cfg, cf, ctx, hist, traj = run("pipe_ava_context", g, fp16, context=True, T=3, max_iter=3,
+                                   NUM_CHUNKS={1: 1, 2: 1, 3: 3}, no_context=False, image_size=(400, 400))
+    sub = cf.float().cpu().numpy()[:, ::4, ::13, ::6, ::6]
+    ref = g["conv_feat_sub"]
+    tol = (2e-2 if fp16 else 1e-4) * np.abs(ref).max()
+    assert np.abs(sub - ref).max() <= tol
+    cref = g["context_feat"]
+    assert ctx.shape == cref.shape
+    assert np.abs(ctx.float().cpu().numpy() - cref).max() <= (2e-2 if fp16 else 1e-4) * np.abs(cref).max()
+    check("pipe_ava_context", g, cfg, cf, hist, traj, fp16)
+
+
+def test_reference_style_driver_calls():
+    """The call pattern of test.py:145-162: module(...) on tensors, .contiguous() slices, ROINet on
+    logical tensors, TwoBranchNet.forward on the 5-D pooled tensor -- results equal the fused path."""
+    import step_b200
+    cfg = synth.make_cfg(fp16=True, T=4, max_iter=1, NUM_CHUNKS={1: 1}, image_size=(112, 112))
+    nets = build(cfg)
+    x = synth.make_clips(2, 16, 112, 112).cuda()
+    tubes = synth.make_proposals(2, 3, 4, 112, 112)
+    with torch.no_grad():
+        cf = nets["base_net"](x)
+        hist, _ = step_b200.inference(cfg, cf, None, nets, 1, tubes)
+        flat, nums = step_b200.tube_utils.flatten_tubes(tubes, batch_idx=True)
+        flat = torch.from_numpy(flat).cuda()
+        pooled = nets["roi_net"](cf[:, 0:4].contiguous(), flat)           # utils.py:48 (NCHW copy path)
+        pooled2 = nets["roi_net"](cf, flat)                                 # channels-last view path
+        assert torch.equal(pooled.float(), pooled2.float())
+        _, C, W, H = pooled.shape
+        prob, loc, first, last, l0, l1, l2 = nets["det_net0"](pooled2.view(-1, 4, C, W, H))
+    assert torch.allclose(prob, hist[0]["pred_prob"][:, 0], atol=1e-6)
+    dec = step_b200.tube_utils.decode_coef(flat.view(-1, 5)[:, 1:].contiguous(), loc.view(-1, 4))
+    assert torch.allclose(dec.view(loc.shape), hist[0]["pred_loc"], atol=1e-4)
+    assert l0.numel() == 1 and float(l0) == 0.0

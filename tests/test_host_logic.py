@@ -1,0 +1,73 @@
+"""CPU: host-side logic of the package -- weight packing, BN folding, the space-to-depth stem
+rewrite, pooling extents, tube list bookkeeping, state-dict key parity."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import model as om
+from oracle import tubes as otubes
+from step_b200 import engine as E
+from step_b200 import synth, tube_utils
+
+
+def test_pool_extent_matches_torch():
+    for size in (7, 8, 13, 14, 16, 25, 28, 56, 112):
+        for k, s in ((3, 2), (3, 1), (1, 1), (2, 2)):
+            lo, hi = E.same_pad(k, s)
+            x = torch.zeros(1, 1, size + lo + hi, 1, 1)
+            ref = F.max_pool3d(x, (k, 1, 1), (s, 1, 1), ceil_mode=True).shape[2]
+            assert E.pool_out(size, k, s)[0] == ref, (size, k, s)
+
+
+def test_pack_conv_weight_layout():
+    w = torch.randn(5, 3, 2, 3, 4)
+    p = E.pack_conv_weight(w, 0)
+    assert p.shape == (5, 24, 4)
+    assert torch.equal(p[2, (1 * 3 + 2) * 4 + 3, :3], w[2, :, 1, 2, 3]) and float(p[..., 3].abs().max()) == 0
+
+
+def test_s2d_stem_is_the_same_convolution():
+    """7x7x7/2 'SAME' conv == 4x4x4/1 conv (pad 1 low, 2 high) over the space-to-depth input."""
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(4, 3, 7, 7, 7, generator=g)
+    x = torch.randn(1, 3, 8, 12, 10, generator=g)
+    ref = F.conv3d(F.pad(x, (2, 3, 2, 3, 2, 3)), w, stride=2)
+    wp = E.pack_stem_s2d(w).float()                       # [4, 64, 32]
+    xs = x.view(1, 3, 4, 2, 6, 2, 5, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(1, 4, 6, 5, 24)  # N,T2,H2,W2,(rt,rh,rw,c)
+    xs = F.pad(xs, (0, 8)).permute(0, 4, 1, 2, 3)          # -> N,32,T2,H2,W2
+    w2 = wp.view(4, 4, 4, 4, 32).permute(0, 4, 1, 2, 3)    # co, c, qt, qh, qw
+    out = F.conv3d(F.pad(xs, (1, 2, 1, 2, 1, 2)), w2)
+    assert out.shape == ref.shape
+    assert torch.allclose(out, ref, atol=2e-2, rtol=1e-2)  # fp16-rounded weights
+
+
+def test_fold_bn_matches_batchnorm():
+    bn = torch.nn.BatchNorm3d(6).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2)
+    s, b = E.fold_bn(bn, None, 6, "cpu")
+    x = torch.randn(2, 6, 3, 4, 5)
+    assert torch.allclose(bn(x), x * s.view(1, -1, 1, 1, 1) + b.view(1, -1, 1, 1, 1), atol=1e-5)
+
+
+def test_flatten_tubes_matches_oracle():
+    rs = np.random.RandomState(0)
+    lst = [rs.rand(2, 3, 4).astype(np.float32), np.zeros((0, 3, 4), np.float32), rs.rand(4, 3, 4).astype(np.float32)]
+    a, na = tube_utils.flatten_tubes(lst, True)
+    b, nb = otubes.flatten_tubes(lst, True)
+    assert np.array_equal(a, b) and na == nb
+
+
+def test_state_dict_keys_match_reference_counts():
+    import step_b200
+    cfg = synth.make_cfg(no_context=False)
+    assert len(step_b200.BaseNet(cfg).state_dict()) == 270       # SURVEY.md section 5 [probe]
+    assert len(step_b200.TwoBranchNet(cfg).state_dict()) == 94
+    assert len(step_b200.ContextNet(cfg).state_dict()) == 72
+    step_b200.BaseNet(cfg).load_state_dict(synth.base_net_state_dict(), strict=True)
+    step_b200.TwoBranchNet(cfg).load_state_dict(synth.head_state_dict(1, cfg), strict=True)
+
+
+def test_oracle_same_pad_table():
+    assert om.same_pad(7, 2) == (2, 3) and om.same_pad(3, 1) == (1, 1) and om.same_pad(3, 2) == (0, 1)
+    assert E.same_pad(7, 2) == (2, 3) and E.same_pad(1, 1) == (0, 0)
