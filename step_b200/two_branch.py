@@ -289,14 +289,24 @@ class TwoBranchNet(nn.Module):
         e1 = min((chunks - 1) * Tc + int(Tc / 2) + half + 1, T)
         first = local_loc[:, s0:s1].contiguous()
         last = local_loc[:, e0:e1].contiguous()
-        base = torch.arange(R, device=cat.device, dtype=torch.int32).view(R, 1) * T
-        rows_f = (base + torch.arange(s0, s1, device=cat.device, dtype=torch.int32).view(1, -1)).reshape(-1).contiguous()
-        rows_l = (base + torch.arange(e0, e1, device=cat.device, dtype=torch.int32).view(1, -1)).reshape(-1).contiguous()
+        rows_f, rows_l = self._chunk_rows(R, T, s0, s1, e0, e1, cat.device)
         w1, b1 = self._reg_weight("neighbor_reg1", code)
         w2n, b2n = self._reg_weight("neighbor_reg2", code)
         E.linear_small_n(lf2.buf, rows_f.numel(), D, D, w1, b1, 4, y=first.view(-1, 4), accumulate=True, row_map=rows_f)
         E.linear_small_n(lf2.buf, rows_l.numel(), D, D, w2n, b2n, 4, y=last.view(-1, 4), accumulate=True, row_map=rows_l)
         return prob, local_loc, first, last
+
+    def _chunk_rows(self, R, T, s0, s1, e0, e1, device):
+        """row indices (into [R*T']) of the first / last chunk frames; cached per shape."""
+        key = (R, T, s0, s1, e0, e1, str(device))
+        c = self.__dict__.get("_rows")
+        if c is None or c[0] != key:
+            base = torch.arange(R, device=device, dtype=torch.int32).view(R, 1) * T
+            f = (base + torch.arange(s0, s1, device=device, dtype=torch.int32).view(1, -1)).reshape(-1).contiguous()
+            l = (base + torch.arange(e0, e1, device=device, dtype=torch.int32).view(1, -1)).reshape(-1).contiguous()
+            self.__dict__["_rows"] = (key, (f, l))
+            c = self.__dict__["_rows"]
+        return c[1]
 
     def _init_net(self):
         self.global_cls.apply(weights_init)

@@ -1,0 +1,46 @@
+"""CPU, world_size 2, gloo: the N>1 host logic of bench.py's clip-parallel mode -- each rank owns a
+disjoint batch, fixed-shape detections are all-gathered once per batch, rank order is preserved and the
+max-over-ranks timing reduction works.  (No GPU kernels are called here.)"""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from step_b200 import synth
+    B, N, C = 2, 3, 6
+    # rank r owns clips [r*B, (r+1)*B): per-rank seed as in bench.py
+    clips = synth.make_clips(B, 4, 8, 8, seed=1234 + rank)
+    det = torch.full((B * N, C + 4), float(rank)) + clips.mean()          # stand-in for [prob | box]
+    gather = torch.empty((world, B * N, C + 4))
+    dist.all_gather_into_tensor(gather.view(-1, C + 4), det)
+    ms = torch.tensor([10.0 + rank])
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    if rank == 0:
+        torch.save({"gather": gather, "ms": ms}, out)
+    dist.destroy_process_group()
+
+
+def test_clip_parallel_gather_two_ranks(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    from step_b200 import synth
+    for rank in range(2):
+        exp = float(rank) + synth.make_clips(2, 4, 8, 8, seed=1234 + rank).mean()
+        assert torch.allclose(r["gather"][rank], torch.full((6, 10), float(exp)))
+    assert float(r["ms"]) == 11.0
