@@ -10,6 +10,7 @@ All compute goes through libstep_b200.so (include/step_b200.h); there is no CPU/
 from .networks import BaseNet, ROINet  # noqa: F401
 from .two_branch import ContextNet, TwoBranchNet  # noqa: F401
 from .inference import inference  # noqa: F401
+from .runner import StepRunner  # noqa: F401
 from . import roi_layers, tube_utils  # noqa: F401
 
-__all__ = ["BaseNet", "ROINet", "TwoBranchNet", "ContextNet", "inference", "roi_layers", "tube_utils"]
+__all__ = ["BaseNet", "ROINet", "TwoBranchNet", "ContextNet", "inference", "StepRunner", "roi_layers", "tube_utils"]

@@ -24,37 +24,24 @@ def _ext_mode(args, i):
     return L.EXT_NONE
 
 
-def inference(args, conv_feat, context_feat, nets, exec_iter, tubes, want_trajectory=True):
-    """Same contract as utils/utils.py:15-131.
+def stage_tubes(tubes, device):
+    """Host list of [n_b, T, 4] numpy tubes -> (flat [R,T,5] fp32, clip_of_tube [R] int32, tubes_nums) on device.
+    flatten_tubes is list bookkeeping only (tube_utils.py:214-246); this is the one H2D of the loop."""
+    flat_np, tubes_nums = flatten_tubes(tubes, batch_idx=True)
+    flat = torch.from_numpy(np.ascontiguousarray(flat_np, dtype=np.float32)).to(device)
+    clip_of_tube = torch.from_numpy(np.repeat(np.arange(len(tubes_nums)), tubes_nums).astype(np.int32)).to(device)
+    return flat, clip_of_tube, tubes_nums
 
-    conv_feat: logical [B, T', 832, H', W'] tensor from BaseNet (a view of our channels-last buffer;
-    any other CUDA tensor of that shape is converted once).  context_feat: [B, 1024, T', 1, 1] or None.
-    nets: {'roi_net': ROINet, 'det_net%d': TwoBranchNet}.  tubes: list of [n_b, T, 4] numpy arrays.
 
-    Returns (history, trajectory): history[i] = {'pred_prob' [R,T_len,cls] (expand view),
-    'pred_loc' [R,T_len,4], 'pred_first_loc', 'pred_last_loc' ([R,T,4] or None), 'tubes_nums'};
-    trajectory[i][b] = (proposals numpy [n_b,T_next,4], pred_class tensor) when want_trajectory.
-    """
-    L.need_cuda(conv_feat)
-    dev = conv_feat.device
-    roi_net = nets['roi_net']
-    head0 = nets['det_net0']
-    code = E.dtype_code(head0.fp16)
-    feat = act_of(conv_feat)
-    if feat is None or feat.code != code:
-        feat = to_act(conv_feat, code)
+def inference_device(args, feat, ctx_all, nets, exec_iter, flat, clip_of_tube, tubes_nums):
+    """Device-only body of the loop (no host<->device traffic, no synchronisation, CUDA-graph
+    capturable).  feat: Act [B,T',H',W',832]; ctx_all: fp32 [B,T',1024] or None; flat [R,T,5].
+    Returns (history, [(flat_next, prob)] per step)."""
+    dev = feat.device
+    code = feat.code
     B, T_total = feat.N, feat.T
-
-    flat_np, tubes_nums = flatten_tubes(tubes, batch_idx=True)  # host list bookkeeping (tube_utils.py:214-246)
-    flat = torch.from_numpy(np.ascontiguousarray(flat_np, dtype=np.float32)).to(dev)
-    clip_of_tube = torch.from_numpy(np.repeat(np.arange(len(tubes_nums)), tubes_nums).astype(np.int32)).to(dev)
     R = flat.shape[0]
-
-    ctx_all = None
-    if not args.no_context:
-        L.need_cuda(context_feat)
-        ctx_all = context_feat.detach().float().reshape(B, context_feat.shape[1], T_total).permute(0, 2, 1).contiguous()
-
+    roi_net = nets['roi_net']
     history, steps = [], []
     width, height = float(args.image_size[0]), float(args.image_size[1])
     decode_nb = args.temporal_mode == "predict"
@@ -83,6 +70,32 @@ def inference(args, conv_feat, context_feat, nets, exec_iter, tubes, want_trajec
                         'tubes_nums': tubes_nums})
         steps.append((flat_next, prob))
         flat = flat_next
+    return history, steps
+
+
+def inference(args, conv_feat, context_feat, nets, exec_iter, tubes, want_trajectory=True):
+    """Same contract as utils/utils.py:15-131.
+
+    conv_feat: logical [B, T', 832, H', W'] tensor from BaseNet (a view of our channels-last buffer;
+    any other CUDA tensor of that shape is converted once).  context_feat: [B, 1024, T', 1, 1] or None.
+    nets: {'roi_net': ROINet, 'det_net%d': TwoBranchNet}.  tubes: list of [n_b, T, 4] numpy arrays.
+
+    Returns (history, trajectory): history[i] = {'pred_prob' [R,T_len,cls] (expand view),
+    'pred_loc' [R,T_len,4], 'pred_first_loc', 'pred_last_loc' ([R,T,4] or None), 'tubes_nums'};
+    trajectory[i][b] = (proposals numpy [n_b,T_next,4], pred_class tensor) when want_trajectory.
+    """
+    L.need_cuda(conv_feat)
+    dev = conv_feat.device
+    code = E.dtype_code(nets['det_net0'].fp16)
+    feat = act_of(conv_feat)
+    if feat is None or feat.code != code:
+        feat = to_act(conv_feat, code)
+    flat, clip_of_tube, tubes_nums = stage_tubes(tubes, dev)
+    ctx_all = None
+    if not args.no_context:
+        L.need_cuda(context_feat)
+        ctx_all = context_feat.detach().float().reshape(feat.N, context_feat.shape[1], feat.T).permute(0, 2, 1).contiguous()
+    history, steps = inference_device(args, feat, ctx_all, nets, exec_iter, flat, clip_of_tube, tubes_nums)
 
     trajectory = []
     if want_trajectory:  # one synchronisation at the very end instead of B per step

@@ -287,8 +287,8 @@ class TwoBranchNet(nn.Module):
         s0, s1 = max(int(Tc / 2) - half, 0), min(int(Tc / 2) + half + 1, T)
         e0 = max((chunks - 1) * Tc + int(Tc / 2) - half, 0)
         e1 = min((chunks - 1) * Tc + int(Tc / 2) + half + 1, T)
-        first = local_loc[:, s0:s1].contiguous()
-        last = local_loc[:, e0:e1].contiguous()
+        first = local_loc[:, s0:s1].clone()   # .clone(): the slice may alias local_loc (two_branch.py:265-266)
+        last = local_loc[:, e0:e1].clone()
         rows_f, rows_l = self._chunk_rows(R, T, s0, s1, e0, e1, cat.device)
         w1, b1 = self._reg_weight("neighbor_reg1", code)
         w2n, b2n = self._reg_weight("neighbor_reg2", code)
