@@ -164,10 +164,12 @@ int step_mean_mid(const void* x, int dtype, int A, int B, int P, int C, int ld, 
  * local_reg, neighbor_reg (two_branch.py:246,261,269-270).  x [M,K] (row stride x_ld) in dtype,
  * w [N,K] in dtype, y fp32 [M, y_ld].  act: 0 none, 1 sigmoid (applied after accumulation).
  * accumulate != 0: y += result.  row_map (optional, device int32 [M]): x row read for output row m
- * (the per-tube context gather of utils/utils.py:54-57). */
+ * (the per-tube context gather of utils/utils.py:54-57).
+ * Split-K with a caller-provided fp32 workspace of step_linear_small_n_workspace_bytes(M,K,N). */
+size_t step_linear_small_n_workspace_bytes(int M, int K, int N);
 int step_linear_small_n(const void* x, int dtype, int M, int K, int x_ld, const void* w, const float* bias,
                         int N, float* y, int y_ld, int act, int accumulate, const int32_t* row_map,
-                        step_stream_t stream);
+                        void* workspace, size_t ws_bytes, step_stream_t stream);
 
 #ifdef __cplusplus
 }

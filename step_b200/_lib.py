@@ -59,7 +59,8 @@ def _declare(lib):
         "step_conv3d_fwd": ([ctypes.POINTER(ConvParams), S], c_int),
         "step_maxpool3d_fwd": ([P, I] + [I] * 21 + [P, I, S], c_int),
         "step_mean_mid": ([P, I, I, I, I, I, I, P, I, S], c_int),
-        "step_linear_small_n": ([P, I, I, I, I, P, P, I, P, I, I, I, P, S], c_int),
+        "step_linear_small_n_workspace_bytes": ([I, I, I], c_size_t),
+        "step_linear_small_n": ([P, I, I, I, I, P, P, I, P, I, I, I, P, P, c_size_t, S], c_int),
         "step_debug_tma_tile": ([ctypes.POINTER(ConvParams), I, I, I, I, I, P, P, P, S], c_int),
     }
     for name, (argtypes, restype) in sigs.items():

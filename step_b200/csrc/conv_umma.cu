@@ -32,6 +32,7 @@ constexpr int kBM = 128;       // UMMA M (cta_group::1)
 constexpr int kMaxBN = 128;    // <= 128 TMEM columns per CTA so two CTAs share an SM
 constexpr int kStages = 3;
 constexpr int kThreads = 192;
+constexpr int kBookBytes = (2 * kStages + 1) * 8 + 8 + 2 * kMaxBN * 4;  // barriers, tmem ptr, scale, shift
 
 struct ConvGeom {
   int mode;
@@ -130,24 +131,25 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-template <int BK>
+template <int BK, bool kHasRes>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvGeom g,
                  const float* __restrict__ scale, const float* __restrict__ shift, const __half* __restrict__ residual,
                  __half* __restrict__ y) {
   constexpr int kABytes = kBM * BK * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B stages][barriers][tmem ptr][scale/shift]
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int b_bytes = g.BN * BK * 2;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kABytes;
-  uint64_t* full_bar = (uint64_t*)(sB + kStages * b_bytes);
+  // carve: [barriers | tmem ptr | scale | shift] (kBookBytes) then the 1024-aligned stage area
+  // [A stages][B stages], re-used by the epilogue as the fp16 output staging tile.
+  uint64_t* full_bar = (uint64_t*)smem_raw;
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint32_t* tmem_ptr_s = (uint32_t*)(tmem_full_bar + 1);
   float* s_scale = (float*)(tmem_ptr_s + 2);
   float* s_shift = s_scale + kMaxBN;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + kBookBytes + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = g.BN * BK * 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kABytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x / g.n_tiles, n_tile = blockIdx.x - m_tile * g.n_tiles;
@@ -259,36 +261,63 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       long long m = m0 + row;
       if (m < g.M) pix = m;
     }
+    // Residual (two_branch.py:79-81): this row's BN halves are fetched into registers *before* waiting for
+    // the accumulator, so the row-strided loads overlap the main loop instead of stalling the epilogue.
+    const __half* rrow = residual ? residual + (pix < 0 ? 0 : (size_t)pix * g.res_ld + g.res_coff + n0) : nullptr;
+    uint4 rreg[kMaxBN / 8];
+    if (kHasRes) {
+#pragma unroll
+      for (int j = 0; j < kMaxBN / 8; ++j) {
+        rreg[j] = make_uint4(0, 0, 0, 0);
+        if (pix >= 0 && j * 8 < g.BN && n0 + j * 8 < g.Cout) rreg[j] = *reinterpret_cast<const uint4*>(rrow + j * 8);
+      }
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-    __half* yrow = y + (pix < 0 ? 0 : (size_t)pix * g.out_ld + g.out_coff + n0);
-    const __half* rrow = residual ? residual + (pix < 0 ? 0 : (size_t)pix * g.res_ld + g.res_coff + n0) : nullptr;
-    for (int c = 0; c < g.BN; c += 16) {
+    // Phase 1: TMEM -> registers -> scale/shift (+residual) (+relu) -> fp16 -> this warp's 32-row slab of the
+    // staging tile (the pipeline stages are idle once tmem_full fired).  Row pitch 2*BN+16 bytes is an odd
+    // multiple of 16, so the 16-byte stores of 8 consecutive rows land in distinct bank groups.
+    const int pitch = g.BN * 2 + 16;
+    uint8_t* slab = smem + (size_t)(lane_grp * 32) * pitch;
+    uint8_t* srow = slab + (size_t)lane * pitch;
+#pragma unroll
+    for (int ci = 0; ci < kMaxBN / 16; ++ci) {
+      const int c = ci * 16;
+      if (c >= g.BN) break;
       uint32_t v[16];
       tmem_ld16(taddr + c, v);
       tmem_ld_wait();
-      if (pix >= 0) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {  // two 8-channel (16-byte) halves
-          const int cc = c + h * 8;
-          if (n0 + cc < g.Cout) {
-            float f[8];
+      for (int h = 0; h < 2; ++h) {  // two 8-channel (16-byte) halves
+        const int cc = c + h * 8;
+        float f[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[h * 8 + k]), s_scale[cc + k], s_shift[cc + k]);
-            if (rrow) {
-              float rv[8];
-              load16(rrow + cc, rv);
+        for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[h * 8 + k]), s_scale[cc + k], s_shift[cc + k]);
+        if (kHasRes) {
+          const __half2* hp = reinterpret_cast<const __half2*>(&rreg[ci * 2 + h]);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) f[k] += rv[k];
-            }
-            if (g.relu) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
-            }
-            store16(yrow + cc, f);
+          for (int k = 0; k < 4; ++k) {
+            float2 rf = __half22float2(hp[k]);
+            f[2 * k] += rf.x; f[2 * k + 1] += rf.y;
           }
         }
+        if (g.relu) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+        }
+        store16(reinterpret_cast<__half*>(srow + cc * 2), f);
+      }
+    }
+    __syncwarp();
+    // Phase 2: coalesced copy-out: consecutive lanes write consecutive 16-byte chunks of an output row.
+    const int cpr = g.BN >> 3;  // 16-byte chunks per row
+    for (int i = lane; i < 32 * cpr; i += 32) {
+      const int rr = i / cpr, ch = i - rr * cpr;
+      const long long rp = __shfl_sync(0xffffffffu, pix, rr);
+      if (rp >= 0 && n0 + ch * 8 < g.Cout) {
+        uint4 val = *reinterpret_cast<const uint4*>(slab + (size_t)rr * pitch + ch * 16);
+        *reinterpret_cast<uint4*>(y + (size_t)rp * g.out_ld + g.out_coff + n0 + ch * 8) = val;
       }
     }
     tc_fence_before();
@@ -487,20 +516,24 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   }
   STEP_CHECK_ARG(m_tiles * g.n_tiles < (1LL << 31), "conv3d(f16): grid too large");
   pl->grid = dim3((unsigned)(m_tiles * g.n_tiles));
-  pl->smem_bytes = 1024 + (size_t)kStages * (kBM * BK * 2 + g.BN * BK * 2) + (2 * kStages + 1) * 8 + 8 + 2 * kMaxBN * 4;
+  {
+    size_t stage_area = (size_t)kStages * (kBM * BK * 2 + g.BN * BK * 2);
+    size_t out_tile = (size_t)kBM * (g.BN * 2 + 16);
+    pl->smem_bytes = kBookBytes + 1024 + (stage_area > out_tile ? stage_area : out_tile);
+  }
   return 0;
 }
 
-template <int BK>
+template <int BK, bool kHasRes>
 static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv3d(f16): smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_umma_kernel<BK><<<pl.grid, kThreads, pl.smem_bytes, s>>>(pl.map_a, pl.map_b, pl.g, p->scale, p->shift,
-                                                               (const __half*)p->residual, (__half*)p->y);
+  conv_umma_kernel<BK, kHasRes><<<pl.grid, kThreads, pl.smem_bytes, s>>>(pl.map_a, pl.map_b, pl.g, p->scale, p->shift,
+                                                                        (const __half*)p->residual, (__half*)p->y);
   STEP_LAUNCH_CHECK("conv_umma_kernel");
   return 0;
 }
@@ -508,9 +541,10 @@ static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t
 int conv3d_umma_launch(const step_conv_params* p, step_stream_t stream) {
   ConvPlan pl;
   if (int rc = build_plan(p, &pl)) return rc;
-  if (pl.BK == 64) return launch_bk<64>(pl, p, cu(stream));
-  if (pl.BK == 32) return launch_bk<32>(pl, p, cu(stream));
-  return launch_bk<16>(pl, p, cu(stream));
+  const bool res = p->residual != nullptr;
+  if (pl.BK == 64) return res ? launch_bk<64, true>(pl, p, cu(stream)) : launch_bk<64, false>(pl, p, cu(stream));
+  if (pl.BK == 32) return res ? launch_bk<32, true>(pl, p, cu(stream)) : launch_bk<32, false>(pl, p, cu(stream));
+  return res ? launch_bk<16, true>(pl, p, cu(stream)) : launch_bk<16, false>(pl, p, cu(stream));
 }
 
 }  // namespace step

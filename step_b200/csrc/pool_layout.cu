@@ -8,37 +8,46 @@
 
 namespace step {
 
+// Thread mapping is the whole optimisation: a CTA owns a compact (TT x TH x TW) tile of output pixels and
+// a 64-byte channel chunk (CV = 4 vectors), thread = (pixel, vector).  The 27 taps of neighbouring
+// outputs then hit the same few KB in L1 instead of re-reading L2 27 times (the pools of
+// Mixed.branch_3, i3dpt.py:150-153, are 3x3x3 / stride 1).  Padded cells hold 0 (ConstantPad3d), cells
+// beyond the padded extent (ceil_mode overhang) are ignored.
+constexpr int kPoolCV = 4;
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ x, int N, int T_, int H, int W, int C,
                                                         int in_ld, int KT, int KH, int KW, int ST, int SH, int SW,
                                                         int PT, int PH, int PW, int pad_hi_t, int pad_hi_h,
                                                         int pad_hi_w, int OT, int OH, int OW, T* __restrict__ y,
-                                                        int out_ld) {
+                                                        int out_ld, int TT, int TH, int TW) {
   constexpr int VN = Vec16<T>::N;
   const int nvec = C / VN;
-  const long long total = (long long)N * OT * OH * OW * nvec;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % nvec);
-    long long pix = idx / nvec;
-    int ow = (int)(pix % OW); long long r = pix / OW;
-    int oh = (int)(r % OH); r /= OH;
-    int ot = (int)(r % OT);
-    int n = (int)(r / OT);
+  const int tiles_w = (OW + TW - 1) / TW, tiles_h = (OH + TH - 1) / TH, tiles_t = (OT + TT - 1) / TT;
+  int r = blockIdx.x;
+  const int w0 = (r % tiles_w) * TW; r /= tiles_w;
+  const int h0 = (r % tiles_h) * TH; r /= tiles_h;
+  const int t0 = (r % tiles_t) * TT;
+  const int n = r / tiles_t;
+  const int cv = blockIdx.y * kPoolCV + (threadIdx.x % kPoolCV);
+  if (cv >= nvec) return;
+  const int npix = TT * TH * TW;
+  for (int p = threadIdx.x / kPoolCV; p < npix; p += blockDim.x / kPoolCV) {
+    const int ow = w0 + p % TW, oh = h0 + (p / TW) % TH, ot = t0 + p / (TW * TH);
+    if (ow >= OW || oh >= OH || ot >= OT) continue;
     float m[VN];
 #pragma unroll
     for (int k = 0; k < VN; ++k) m[k] = -3.402823466e+38f;
     bool touches_pad = false, any = false;
     for (int kt = 0; kt < KT; ++kt) {
-      int t = ot * ST + kt - PT;          // coordinate in the un-padded tensor
-      if (t >= T_ + pad_hi_t) continue;   // beyond the padded extent (ceil_mode overhang)
-      bool tp = (t < 0) || (t >= T_);
+      const int t = ot * ST + kt - PT;          // coordinate in the un-padded tensor
+      if (t >= T_ + pad_hi_t) continue;         // beyond the padded extent (ceil_mode overhang)
+      const bool tp = (t < 0) || (t >= T_);
       for (int kh = 0; kh < KH; ++kh) {
-        int h = oh * SH + kh - PH;
+        const int h = oh * SH + kh - PH;
         if (h >= H + pad_hi_h) continue;
-        bool hp = (h < 0) || (h >= H);
+        const bool hp = (h < 0) || (h >= H);
         for (int kw = 0; kw < KW; ++kw) {
-          int w = ow * SW + kw - PW;
+          const int w = ow * SW + kw - PW;
           if (w >= W + pad_hi_w) continue;
           if (tp || hp || w < 0 || w >= W) { touches_pad = true; continue; }
           float v[VN];
@@ -53,7 +62,7 @@ __global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ x,
 #pragma unroll
       for (int k = 0; k < VN; ++k) m[k] = fmaxf(m[k], 0.0f);
     }
-    store16(y + (size_t)pix * out_ld + cv * VN, m);
+    store16(y + ((((size_t)n * OT + ot) * OH + oh) * OW + ow) * out_ld + cv * VN, m);
   }
 }
 
@@ -85,26 +94,44 @@ __global__ void clip_to_ndhwc_kernel(const float* __restrict__ clip, int N, int 
   }
 }
 
-// clip [N,T,Cc,H,W] fp32 -> s2d [N,T/2,H/2,W/2,ld] f16, channel ((rt*2+rh)*2+rw)*Cc + c
-__global__ void clip_to_s2d_kernel(const float* __restrict__ clip, int N, int T_, int Cc, int H, int W,
-                                   __half* __restrict__ out, int ld) {
+// clip [N,T,Cc,H,W] fp32 -> s2d [N,T/2,H/2,W/2,ld] f16, channel ((rt*2+rh)*2+rw)*Cc + c.
+// One CTA per output row (n, t2, h2): the 4*Cc input rows it needs are read coalesced into smem, then
+// each thread emits one 16-byte (8-channel) vector of one output pixel: both sides fully coalesced.
+__global__ void __launch_bounds__(256) clip_to_s2d_kernel(const float* __restrict__ clip, int N, int T_, int Cc, int H,
+                                                          int W, __half* __restrict__ out, int ld) {
+  extern __shared__ float rows[];  // [rt][rh][c][W]
   const int T2 = T_ / 2, H2 = H / 2, W2 = W / 2;
-  long long total = (long long)N * T2 * H2 * W2;
-  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
-       pix += (long long)gridDim.x * blockDim.x) {
-    int w2 = (int)(pix % W2); long long r = pix / W2;
-    int h2 = (int)(r % H2); r /= H2;
-    int t2 = (int)(r % T2);
-    int n = (int)(r / T2);
-    __half* o = out + (size_t)pix * ld;
-    int ch = 0;
-    for (int rt = 0; rt < 2; ++rt)
-      for (int rh = 0; rh < 2; ++rh)
-        for (int rw = 0; rw < 2; ++rw)
-          for (int c = 0; c < Cc; ++c, ++ch)
-            o[ch] = __float2half_rn(
-                clip[((((size_t)n * T_ + 2 * t2 + rt) * Cc + c) * H + 2 * h2 + rh) * W + 2 * w2 + rw]);
-    for (; ch < ld; ++ch) o[ch] = __float2half_rn(0.0f);
+  int r = blockIdx.x;
+  const int h2 = r % H2; r /= H2;
+  const int t2 = r % T2;
+  const int n = r / T2;
+  // 4*Cc input rows, each W contiguous floats: no per-element div/mod (runtime divisors are ~40 instructions)
+  for (int rt = 0; rt < 2; ++rt)
+    for (int rh = 0; rh < 2; ++rh)
+      for (int c = 0; c < Cc; ++c) {
+        const float* src = clip + ((((size_t)n * T_ + 2 * t2 + rt) * Cc + c) * H + 2 * h2 + rh) * W;
+        float* dst = rows + ((rt * 2 + rh) * Cc + c) * W;
+        for (int w = threadIdx.x; w < W; w += blockDim.x) dst[w] = src[w];
+      }
+  __syncthreads();
+  const int nvec = ld / 8;
+  __half* orow = out + (((size_t)n * T2 + t2) * H2 + h2) * W2 * ld;
+  // thread = (w2, 8-channel vector); channel ch = ((rt*2+rh)*2+rw)*Cc + c  ->  smem row (rt,rh,c), column 2*w2+rw
+  const int cvs = threadIdx.x % nvec;          // blockDim.x is a multiple of nvec (ld = 32 -> 4)
+  int srow[8], scol[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = cvs * 8 + k;
+    if (ch < 8 * Cc) {
+      const int c = ch % Cc, q = ch / Cc;      // q = (rt*2+rh)*2+rw
+      srow[k] = ((q >> 1) * Cc + c) * W; scol[k] = q & 1;
+    } else { srow[k] = -1; scol[k] = 0; }
+  }
+  for (int w2 = threadIdx.x / nvec; w2 < W2; w2 += blockDim.x / nvec) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = srow[k] >= 0 ? rows[srow[k] + 2 * w2 + scol[k]] : 0.0f;
+    store16(orow + (size_t)w2 * ld + cvs * 8, v);
   }
 }
 
@@ -139,35 +166,55 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int S, int C, 
   }
 }
 
-// Small-N linear: one CTA per row-pair block; each warp owns output columns, lanes stride K.
-// y[m,n] = act(sum_k x[m,k] w[n,k] + b[n]).  K is long (12544), N tiny (4 / 60): the x row is read
-// once per CTA from HBM, w stays in L2.
-constexpr int kLinRows = 4;
+// Small-N linear layers (global_cls N=60, local_reg / neighbor_reg N=4; K = 12544), split-K:
+// CTA (kc, mt) stages an 8-row x KC-column tile of x in shared memory (fp32) and each warp sweeps
+// output columns n = warp, warp+8, ...: lanes stream w[n, chunk] with 16-byte loads and multiply against
+// the 8 staged rows.  Partials go to a [ksplit, M, N] workspace; linear_reduce_kernel sums them in a
+// fixed order (deterministic), adds bias, optionally accumulates into y and applies the activation.
+constexpr int kLinRows = 8;
+constexpr int kLinKC = 512;
 template <typename T>
-__global__ void __launch_bounds__(256) linear_small_n_kernel(const T* __restrict__ x, int M, int K, int x_ld,
-                                                             const T* __restrict__ w, const float* __restrict__ bias,
-                                                             int N, float* __restrict__ y, int y_ld, int act,
-                                                             int accumulate, const int32_t* __restrict__ row_map) {
+__global__ void __launch_bounds__(256) linear_splitk_kernel(const T* __restrict__ x, int M, int K, int x_ld,
+                                                            const T* __restrict__ w, int N,
+                                                            const int32_t* __restrict__ row_map,
+                                                            float* __restrict__ partial) {
   constexpr int VN = Vec16<T>::N;
-  const int m0 = blockIdx.x * kLinRows;
+  __shared__ __align__(16) float xs[kLinRows][kLinKC];
+  const int kc = blockIdx.x, m0 = blockIdx.y * kLinRows;
+  const int k0 = kc * kLinKC;
+  const int klen = min(kLinKC, K - k0);  // multiple of VN
+  for (int i = threadIdx.x; i < kLinRows * (kLinKC / VN); i += blockDim.x) {
+    const int r = i / (kLinKC / VN), kv = i - r * (kLinKC / VN);
+    float v[VN];
+#pragma unroll
+    for (int k = 0; k < VN; ++k) v[k] = 0.0f;
+    if (m0 + r < M && kv * VN < klen) {
+      const int xr = row_map ? row_map[m0 + r] : m0 + r;
+      load16(x + (size_t)xr * x_ld + k0 + kv * VN, v);
+    }
+#pragma unroll
+    for (int k = 0; k < VN; ++k) xs[r][kv * VN + k] = v[k];
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int kvec = K / VN;
   for (int n = warp; n < N; n += nwarps) {
     float acc[kLinRows];
 #pragma unroll
     for (int r = 0; r < kLinRows; ++r) acc[r] = 0.0f;
-    const T* wr = w + (size_t)n * K;
-    for (int kv = lane; kv < kvec; kv += 32) {
+    const T* wr = w + (size_t)n * K + k0;
+    for (int kv = lane; kv * VN < klen; kv += 32) {
       float wv[VN];
       load16(wr + kv * VN, wv);
 #pragma unroll
       for (int r = 0; r < kLinRows; ++r) {
-        if (m0 + r < M) {
-          float xv[VN];
-          const int xr = row_map ? row_map[m0 + r] : m0 + r;
-          load16(x + (size_t)xr * x_ld + kv * VN, xv);
+        const float4* xp = reinterpret_cast<const float4*>(&xs[r][kv * VN]);
 #pragma unroll
-          for (int k = 0; k < VN; ++k) acc[r] = fmaf(xv[k], wv[k], acc[r]);
+        for (int q = 0; q < VN / 4; ++q) {
+          float4 xv = xp[q];
+          acc[r] = fmaf(xv.x, wv[4 * q + 0], acc[r]);
+          acc[r] = fmaf(xv.y, wv[4 * q + 1], acc[r]);
+          acc[r] = fmaf(xv.z, wv[4 * q + 2], acc[r]);
+          acc[r] = fmaf(xv.w, wv[4 * q + 3], acc[r]);
         }
       }
     }
@@ -176,15 +223,24 @@ __global__ void __launch_bounds__(256) linear_small_n_kernel(const T* __restrict
       float v = acc[r];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && m0 + r < M) {
-        v += bias ? bias[n] : 0.0f;
-        float* dst = y + (size_t)(m0 + r) * y_ld + n;
-        if (accumulate) v += *dst;
-        if (act == 1) v = 1.0f / (1.0f + expf(-v));
-        *dst = v;
-      }
+      if (lane == 0 && m0 + r < M) partial[((size_t)kc * M + m0 + r) * N + n] = v;
     }
   }
+}
+
+__global__ void linear_reduce_kernel(const float* __restrict__ partial, int ksplit, int M, int N,
+                                     const float* __restrict__ bias, float* __restrict__ y, int y_ld, int act,
+                                     int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  int m = i / N, n = i - m * N;
+  float v = 0.0f;
+  for (int s = 0; s < ksplit; ++s) v += partial[((size_t)s * M + m) * N + n];
+  v += bias ? bias[n] : 0.0f;
+  float* dst = y + (size_t)m * y_ld + n;
+  if (accumulate) v += *dst;
+  if (act == 1) v = 1.0f / (1.0f + expf(-v));
+  *dst = v;
 }
 
 static int grid_for(long long total, int block) {
@@ -206,15 +262,19 @@ extern "C" int step_maxpool3d_fwd(const void* x, int dtype, int N, int T, int H,
   STEP_CHECK_ARG(x && y && N > 0 && T > 0 && H > 0 && W > 0, "maxpool3d: bad shape/pointer");
   STEP_CHECK_ARG(C % vn == 0 && in_ld % vn == 0 && out_ld % vn == 0, "maxpool3d: C/ld must be multiples of %d", vn);
   STEP_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "maxpool3d: pointers must be 16-byte aligned");
-  long long total = (long long)N * OT * OH * OW * (C / vn);
+  // tile: up to 4 x 8 x 8 output pixels (whole rows on the small maps), 64-byte channel chunks
+  const int TW = OW < 8 ? OW : (OW % 7 == 0 ? 7 : 8), TH = OH < 8 ? OH : (OH % 7 == 0 ? 7 : 8), TT = OT < 4 ? OT : 4;
+  long long tiles = (long long)N * ceil_div(OT, TT) * ceil_div(OH, TH) * ceil_div(OW, TW);
+  STEP_CHECK_ARG(tiles < (1LL << 31), "maxpool3d: too many tiles");
+  dim3 grid((unsigned)tiles, ceil_div(C / vn, kPoolCV));
   if (dtype == STEP_F16)
-    maxpool3d_kernel<__half><<<grid_for(total, 256), 256, 0, cu(stream)>>>(
-        (const __half*)x, N, T, H, W, C, in_ld, KT, KH, KW, ST, SH, SW, PT, PH, PW, pad_hi_t, pad_hi_h, pad_hi_w, OT,
-        OH, OW, (__half*)y, out_ld);
+    maxpool3d_kernel<__half><<<grid, 256, 0, cu(stream)>>>((const __half*)x, N, T, H, W, C, in_ld, KT, KH, KW, ST, SH, SW,
+                                                           PT, PH, PW, pad_hi_t, pad_hi_h, pad_hi_w, OT, OH, OW,
+                                                           (__half*)y, out_ld, TT, TH, TW);
   else
-    maxpool3d_kernel<float><<<grid_for(total, 256), 256, 0, cu(stream)>>>(
-        (const float*)x, N, T, H, W, C, in_ld, KT, KH, KW, ST, SH, SW, PT, PH, PW, pad_hi_t, pad_hi_h, pad_hi_w, OT,
-        OH, OW, (float*)y, out_ld);
+    maxpool3d_kernel<float><<<grid, 256, 0, cu(stream)>>>((const float*)x, N, T, H, W, C, in_ld, KT, KH, KW, ST, SH, SW, PT,
+                                                          PH, PW, pad_hi_t, pad_hi_h, pad_hi_w, OT, OH, OW, (float*)y,
+                                                          out_ld, TT, TH, TW);
   STEP_LAUNCH_CHECK("maxpool3d_kernel");
   return 0;
 }
@@ -254,8 +314,11 @@ extern "C" int step_clip_to_s2d_f16(const float* clip, int N, int T, int Cc, int
                                     step_stream_t stream) {
   STEP_CHECK_ARG(clip && out && N > 0 && T > 0 && Cc > 0 && H > 0 && W > 0, "clip_to_s2d: bad args");
   STEP_CHECK_ARG(T % 2 == 0 && H % 2 == 0 && W % 2 == 0 && ld >= 8 * Cc, "clip_to_s2d: T,H,W must be even, ld >= 8*Cc");
-  long long total = (long long)N * (T / 2) * (H / 2) * (W / 2);
-  clip_to_s2d_kernel<<<grid_for(total, 256), 256, 0, cu(stream)>>>(clip, N, T, Cc, H, W, (__half*)out, ld);
+  STEP_CHECK_ARG(ld % 8 == 0 && 256 % (ld / 8) == 0 && (size_t)4 * Cc * W * sizeof(float) <= 48 * 1024, "clip_to_s2d: ld must divide 2048, row tile must fit 48 KB smem");
+  STEP_CHECK_ARG(((uintptr_t)out & 15) == 0, "clip_to_s2d: out must be 16-byte aligned");
+  long long rows = (long long)N * (T / 2) * (H / 2);
+  STEP_CHECK_ARG(rows < (1LL << 31), "clip_to_s2d: too many rows");
+  clip_to_s2d_kernel<<<(unsigned)rows, 256, (size_t)4 * Cc * W * sizeof(float), cu(stream)>>>(clip, N, T, Cc, H, W, (__half*)out, ld);
   STEP_LAUNCH_CHECK("clip_to_s2d_kernel");
   return 0;
 }
@@ -288,22 +351,35 @@ extern "C" int step_nchw_to_nhwc(const float* in, int N, int S, int C, void* out
   return 0;
 }
 
+extern "C" size_t step_linear_small_n_workspace_bytes(int M, int K, int N) {
+  if (M <= 0 || K <= 0 || N <= 0) return 0;
+  return (size_t)ceil_div(K, kLinKC) * M * N * sizeof(float);
+}
+
 extern "C" int step_linear_small_n(const void* x, int dtype, int M, int K, int x_ld, const void* w, const float* bias,
                                    int N, float* y, int y_ld, int act, int accumulate, const int32_t* row_map,
-                                   step_stream_t stream) {
+                                   void* workspace, size_t ws_bytes, step_stream_t stream) {
   const int vn = dtype == STEP_F16 ? 8 : 4;
   STEP_CHECK_ARG(dtype == STEP_F16 || dtype == STEP_F32, "linear_small_n: bad dtype");
   STEP_CHECK_ARG(x && w && y && M >= 0 && K > 0 && N > 0 && N <= 64 && y_ld >= N, "linear_small_n: bad args (N <= 64)");
   STEP_CHECK_ARG(K % vn == 0 && x_ld % vn == 0, "linear_small_n: K and x_ld must be multiples of %d", vn);
   STEP_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0, "linear_small_n: pointers must be 16-byte aligned");
   if (M == 0) return 0;
-  int grid = ceil_div(M, kLinRows);
+  const int ksplit = ceil_div(K, kLinKC);
+  if (!workspace || ws_bytes < step_linear_small_n_workspace_bytes(M, K, N))
+    return fail(STEP_E_WORKSPACE, "linear_small_n: workspace %zu < %zu", ws_bytes, step_linear_small_n_workspace_bytes(M, K, N));
+  dim3 grid(ksplit, ceil_div(M, kLinRows));
+  STEP_CHECK_ARG(grid.y <= 65535, "linear_small_n: M too large");
+  const int threads = N >= 8 ? 256 : 32 * N;
   if (dtype == STEP_F16)
-    linear_small_n_kernel<__half><<<grid, 256, 0, cu(stream)>>>((const __half*)x, M, K, x_ld, (const __half*)w, bias, N,
-                                                                y, y_ld, act, accumulate, row_map);
+    linear_splitk_kernel<__half><<<grid, threads, 0, cu(stream)>>>((const __half*)x, M, K, x_ld, (const __half*)w, N,
+                                                                    row_map, (float*)workspace);
   else
-    linear_small_n_kernel<float><<<grid, 256, 0, cu(stream)>>>((const float*)x, M, K, x_ld, (const float*)w, bias, N, y,
-                                                               y_ld, act, accumulate, row_map);
-  STEP_LAUNCH_CHECK("linear_small_n_kernel");
+    linear_splitk_kernel<float><<<grid, threads, 0, cu(stream)>>>((const float*)x, M, K, x_ld, (const float*)w, N,
+                                                                   row_map, (float*)workspace);
+  STEP_LAUNCH_CHECK("linear_splitk_kernel");
+  linear_reduce_kernel<<<ceil_div((long long)M * N, 256), 256, 0, cu(stream)>>>((const float*)workspace, ksplit, M, N, bias,
+                                                                               y, y_ld, act, accumulate);
+  STEP_LAUNCH_CHECK("linear_reduce_kernel");
   return 0;
 }

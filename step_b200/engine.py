@@ -184,6 +184,9 @@ def mean_mid(x_ptr, code, A, B, P, C, ld, device, out_code=L.F32):
 def linear_small_n(x, M, K, x_ld, w, bias, N, y=None, act=0, accumulate=False, row_map=None):
     if y is None:
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    nbytes = L.lib().step_linear_small_n_workspace_bytes(M, K, N)
+    ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=x.device)
     L.check(L.lib().step_linear_small_n(L.ptr(x), L.dt(x), M, K, x_ld, L.ptr(w), L.ptr(bias), N, L.ptr(y),
-                                        y.shape[1], act, 1 if accumulate else 0, L.ptr(row_map), L.stream()))
+                                        y.shape[1], act, 1 if accumulate else 0, L.ptr(row_map), L.ptr(ws), nbytes,
+                                        L.stream()))
     return y
