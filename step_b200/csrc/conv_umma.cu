@@ -21,6 +21,7 @@
 // Pipeline: kStages smem stages, full/empty mbarriers; 2 CTAs per SM overlap one CTA's epilogue with
 // the other's main loop.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -29,8 +30,9 @@ namespace step {
 enum { A_LINEAR = 1, A_BOX = 2, A_IM2COL = 3 };
 
 constexpr int kBM = 128;       // UMMA M (cta_group::1)
-constexpr int kMaxBN = 128;    // <= 128 TMEM columns per CTA so two CTAs share an SM
-constexpr int kStages = 3;
+constexpr int kMaxBN = 256;    // <= 256 TMEM columns per CTA so two CTAs (2 x 256 = all 512 columns) share an SM
+constexpr int kMaxBNRes = 128; // residual rows are prefetched into registers: keep that to 16 x uint4
+constexpr int kStages = 3;     // BN <= 128: 3 stages of <= 32 KB; BN > 128: 2 stages of <= 48 KB (<= 96 KB per CTA)
 constexpr int kThreads = 192;
 constexpr int kBookBytes = (2 * kStages + 1) * 8 + 8 + 2 * kMaxBN * 4;  // barriers, tmem ptr, scale, shift
 
@@ -39,6 +41,7 @@ struct ConvGeom {
   int taps, KT, KH, KW, PT, PH, PW;
   int kblocks_per_tap;          // ceil(Cin / BK)
   int BN, n_tiles;              // N tile (multiple of 16) and count
+  int n_stages;                 // smem pipeline depth used by the one-tile-per-CTA kernel
   int Cout, out_ld, out_coff, res_ld, res_coff, relu;
   int OT, OH, OW, Nimg;
   long long M;                  // Nimg*OT*OH*OW
@@ -149,7 +152,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + kBookBytes + 1023) & ~(uintptr_t)1023);
   const int b_bytes = g.BN * BK * 2;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kABytes;
+  uint8_t* sB = smem + g.n_stages * kABytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x / g.n_tiles, n_tile = blockIdx.x - m_tile * g.n_tiles;
@@ -222,7 +225,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tma_load_im2col_5d(&map_a, &full_bar[stage], a_dst, c0, iw, ih, it, in_, (uint16_t)kw, (uint16_t)kh, (uint16_t)kt);
           }
           tma_load_3d(&map_b, &full_bar[stage], b_dst, c0, tap, n0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -244,7 +247,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulator complete
       }
       __syncwarp();
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -264,10 +267,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // Residual (two_branch.py:79-81): this row's BN halves are fetched into registers *before* waiting for
     // the accumulator, so the row-strided loads overlap the main loop instead of stalling the epilogue.
     const __half* rrow = residual ? residual + (pix < 0 ? 0 : (size_t)pix * g.res_ld + g.res_coff + n0) : nullptr;
-    uint4 rreg[kMaxBN / 8];
+    uint4 rreg[kMaxBNRes / 8];
     if (kHasRes) {
 #pragma unroll
-      for (int j = 0; j < kMaxBN / 8; ++j) {
+      for (int j = 0; j < kMaxBNRes / 8; ++j) {
         rreg[j] = make_uint4(0, 0, 0, 0);
         if (pix >= 0 && j * 8 < g.BN && n0 + j * 8 < g.Cout) rreg[j] = *reinterpret_cast<const uint4*>(rrow + j * 8);
       }
@@ -294,7 +297,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         float f[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[h * 8 + k]), s_scale[cc + k], s_shift[cc + k]);
-        if (kHasRes) {
+        if (kHasRes && ci < kMaxBNRes / 16) {
           const __half2* hp = reinterpret_cast<const __half2*>(&rreg[ci * 2 + h]);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -326,6 +329,247 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+// ---- persistent variant ----------------------------------------------------------------------
+// One CTA per SM loops over output tiles.  Three overlapped pipelines: smem stages (TMA <-> MMA),
+// two TMEM accumulators (MMA <-> epilogue: the MMA warp starts tile i+1 while the epilogue drains
+// tile i), and per-warp epilogue staging slabs.  TMEM allocation, barrier setup and descriptor
+// prefetch are paid once per CTA instead of once per tile, which is what the many small-K layers of
+// the network (1x1x1 branches, the 256->1024 bottleneck outputs) were bound by.
+constexpr int kStagesP = 5;
+constexpr int kEpiWarps = 8;                       // (lane quarter) x (column half)
+constexpr int kThreadsP = 64 + kEpiWarps * 32;     // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int kMaxBNP = 128;                       // the persistent kernel keeps 2 x 128-column accumulators
+constexpr int kSlabCols = kMaxBNP / 2;             // columns one epilogue warp handles per tile
+constexpr int kSlabPitch = kSlabCols * 2 + 16;     // bytes, odd multiple of 16 -> conflict-free 16B stores
+constexpr int kBookBytesP = 4096 + 8 * 2 * kSlabCols * 4;  // barriers etc. (first 4 KB) + per-warp scale/shift
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileOrigin {
+  long long m0;
+  int n0, bn, bt0, bh0, bw0;
+};
+
+__device__ __forceinline__ TileOrigin tile_origin(const ConvGeom& g, int tile) {
+  TileOrigin o;
+  const int m_tile = tile / g.n_tiles;
+  o.n0 = (tile - m_tile * g.n_tiles) * g.BN;
+  o.m0 = (long long)m_tile * kBM;
+  o.bn = o.bt0 = o.bh0 = o.bw0 = 0;
+  if (g.mode == A_BOX) {
+    int r = m_tile;
+    o.bw0 = (r % g.tiles_w) * g.bw; r /= g.tiles_w;
+    o.bh0 = (r % g.tiles_h) * g.bh; r /= g.tiles_h;
+    o.bt0 = (r % g.tiles_t) * g.bt; o.bn = r / g.tiles_t;
+  }
+  return o;
+}
+
+template <int BK, bool kHasRes>
+__global__ void __launch_bounds__(kThreadsP, 1)
+conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvGeom g,
+                         int total_tiles, const float* __restrict__ scale, const float* __restrict__ shift,
+                         const __half* __restrict__ residual, __half* __restrict__ y) {
+  constexpr int kABytes = kBM * BK * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint64_t* full_bar = (uint64_t*)smem_raw;
+  uint64_t* empty_bar = full_bar + kStagesP;
+  uint64_t* tfull_bar = empty_bar + kStagesP;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_ptr_s = (uint32_t*)(tempty_bar + 2);
+  float* ss_all = (float*)(smem_raw + 4096);    // [kEpiWarps][2][kSlabCols]
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + kBookBytesP + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = g.BN * BK * 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStagesP * kABytes;
+  uint8_t* slabs = sB + kStagesP * b_bytes;     // [kEpiWarps][32 rows][kSlabPitch]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = g.taps * g.kblocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStagesP; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiWarps); }
+    fence_barrier_init();
+  }
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)g.BN) ncols <<= 1;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(2 * ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const uint32_t tx_bytes = (uint32_t)(g.a_bytes + b_bytes);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileOrigin o = tile_origin(g, tile);
+        int iw = 0, ih = 0, it = 0, in_ = 0;
+        if (g.mode == A_IM2COL) {
+          long long r = o.m0;
+          iw = (int)(r % g.OW); r /= g.OW;
+          ih = (int)(r % g.OH); r /= g.OH;
+          it = (int)(r % g.OT); in_ = (int)(r / g.OT);
+          iw -= g.PW; ih -= g.PH; it -= g.PT;
+        }
+        for (int tap = 0; tap < g.taps; ++tap) {
+          const int kw = tap % g.KW, kh = (tap / g.KW) % g.KH, kt = tap / (g.KW * g.KH);
+          for (int kc = 0; kc < g.kblocks_per_tap; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
+            void* a_dst = sA + stage * kABytes;
+            void* b_dst = sB + stage * b_bytes;
+            const int c0 = kc * BK;
+            if (g.mode == A_LINEAR) {
+              tma_load_2d(&map_a, &full_bar[stage], a_dst, c0, (int)o.m0);
+            } else if (g.mode == A_BOX) {
+              tma_load_5d(&map_a, &full_bar[stage], a_dst, c0, o.bw0 + kw - g.PW, o.bh0 + kh - g.PH, o.bt0 + kt - g.PT, o.bn);
+            } else {
+              tma_load_im2col_5d(&map_a, &full_bar[stage], a_dst, c0, iw, ih, it, in_, (uint16_t)kw, (uint16_t)kh, (uint16_t)kt);
+            }
+            tma_load_3d(&map_b, &full_bar[stage], b_dst, c0, tap, o.n0);
+            if (++stage == kStagesP) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tempty_bar[buf], tphase ^ 1);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)buf * ncols;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(sA + stage * kABytes), b_addr = smem_u32(sB + stage * b_bytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(tmem_d, make_smem_desc<BK>(a_addr + k * 32), make_smem_desc<BK>(b_addr + k * 32), g.idesc,
+                     (kb | k) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[buf]);
+        }
+        __syncwarp();
+        if (++stage == kStagesP) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
+    const int lane_grp = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                      // which column half of the tile
+    const int chunks = g.BN >> 4;                  // 16-column chunks in the tile
+    const int ch_begin = half ? (chunks + 1) / 2 : 0;
+    const int ch_end = half ? chunks : (chunks + 1) / 2;
+    const int col0 = ch_begin * 16, ncol = (ch_end - ch_begin) * 16;
+    float* s_scale = ss_all + (size_t)ew * 2 * kSlabCols;
+    float* s_shift = s_scale + kSlabCols;
+    uint8_t* slab = slabs + (size_t)ew * 32 * kSlabPitch;
+    uint8_t* srow = slab + (size_t)lane * kSlabPitch;
+    const int row = lane_grp * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      const TileOrigin o = tile_origin(g, tile);
+      long long pix = -1;
+      if (g.mode == A_BOX) {
+        int dw = row % g.bw, r = row / g.bw;
+        int dh = r % g.bh, dt = r / g.bh;
+        int ow = o.bw0 + dw, oh = o.bh0 + dh, ot = o.bt0 + dt;
+        if (dt < g.bt && ow < g.OW && oh < g.OH && ot < g.OT) pix = (((long long)o.bn * g.OT + ot) * g.OH + oh) * g.OW + ow;
+      } else {
+        long long m = o.m0 + row;
+        if (m < g.M) pix = m;
+      }
+      const int nbase = o.n0 + col0;               // first output channel this warp handles
+      for (int i = lane; i < ncol; i += 32) {
+        const int c = nbase + i;
+        s_scale[i] = (scale && c < g.Cout) ? scale[c] : 1.0f;
+        s_shift[i] = (shift && c < g.Cout) ? shift[c] : 0.0f;
+      }
+      uint4 rreg[kSlabCols / 8];
+      if (kHasRes) {
+        const __half* rrow = residual + (pix < 0 ? 0 : (size_t)pix * g.res_ld + g.res_coff + nbase);
+#pragma unroll
+        for (int j = 0; j < kSlabCols / 8; ++j) {
+          rreg[j] = make_uint4(0, 0, 0, 0);
+          if (pix >= 0 && j * 8 < ncol && nbase + j * 8 < g.Cout) rreg[j] = *reinterpret_cast<const uint4*>(rrow + j * 8);
+        }
+      }
+      __syncwarp();
+      mbar_wait(&tfull_bar[buf], tphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)buf * ncols + (uint32_t)col0;
+#pragma unroll
+      for (int ci = 0; ci < kSlabCols / 16; ++ci) {
+        const int c = ci * 16;
+        if (c >= ncol) break;
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int cc = c + h * 8;
+          float f[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[h * 8 + k]), s_scale[cc + k], s_shift[cc + k]);
+          if (kHasRes) {
+            const __half2* hp = reinterpret_cast<const __half2*>(&rreg[ci * 2 + h]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float2 rf = __half22float2(hp[k]);
+              f[2 * k] += rf.x; f[2 * k + 1] += rf.y;
+            }
+          }
+          if (g.relu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+          }
+          store16(reinterpret_cast<__half*>(srow + cc * 2), f);
+        }
+      }
+      // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      // coalesced copy-out of this warp's 32 x ncol slab
+      const int cpr = ncol >> 3;
+      for (int i = lane; i < 32 * cpr; i += 32) {
+        const int rr = i / cpr, ch = i - rr * cpr;
+        const long long rp = __shfl_sync(0xffffffffu, pix, rr);
+        if (rp >= 0 && nbase + ch * 8 < g.Cout) {
+          uint4 val = *reinterpret_cast<const uint4*>(slab + (size_t)rr * kSlabPitch + ch * 16);
+          *reinterpret_cast<uint4*>(y + (size_t)rp * g.out_ld + g.out_coff + nbase + ch * 8) = val;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ncols) : "memory");
   }
 }
 
@@ -418,6 +662,15 @@ static void pick_box(int OW, int OH, int OT, int* bw, int* bh, int* bt) {
     }
 }
 
+static int conv_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("STEP_B200_CONV");
+    v = (e && e[0] == '1') ? 1 : 2;   // 1 = one tile per CTA (2 CTAs/SM), 2 = persistent (default)
+  }
+  return v;
+}
+
 struct ConvPlan {
   CUtensorMap map_a, map_b;
   ConvGeom g;
@@ -448,8 +701,14 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   pl->BK = pick_bk(p->Cin);
   const int BK = pl->BK;
   g.kblocks_per_tap = (p->Cin + BK - 1) / BK;
-  g.n_tiles = (p->Cout + kMaxBN - 1) / kMaxBN;
-  g.BN = (((p->Cout + g.n_tiles - 1) / g.n_tiles) + 15) / 16 * 16;
+  {
+    // N tile: as wide as the accumulator allows -- every N tile re-reads the whole A operand through L2,
+    // which is what bounds the k>1 layers.  Residual layers and the persistent (1x1) variant stay <= 128.
+    const int cap = (p->residual || (taps == 1 && conv_variant() == 2)) ? kMaxBNRes : kMaxBN;
+    g.n_tiles = (p->Cout + cap - 1) / cap;
+    g.BN = (((p->Cout + g.n_tiles - 1) / g.n_tiles) + 15) / 16 * 16;
+    g.n_stages = g.BN > 128 ? 2 : 3;
+  }
   g.Cout = p->Cout; g.out_ld = p->out_ld; g.out_coff = p->out_coff; g.res_ld = p->res_ld; g.res_coff = p->res_coff;
   g.relu = p->relu;
   g.OT = p->OT; g.OH = p->OH; g.OW = p->OW; g.Nimg = p->N;
@@ -517,7 +776,7 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   STEP_CHECK_ARG(m_tiles * g.n_tiles < (1LL << 31), "conv3d(f16): grid too large");
   pl->grid = dim3((unsigned)(m_tiles * g.n_tiles));
   {
-    size_t stage_area = (size_t)kStages * (kBM * BK * 2 + g.BN * BK * 2);
+    size_t stage_area = (size_t)g.n_stages * (kBM * BK * 2 + g.BN * BK * 2);
     size_t out_tile = (size_t)kBM * (g.BN * 2 + 16);
     pl->smem_bytes = kBookBytes + 1024 + (stage_area > out_tile ? stage_area : out_tile);
   }
@@ -538,10 +797,35 @@ static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t
   return 0;
 }
 
+template <int BK, bool kHasRes>
+static int launch_persist(const ConvPlan& pl, const step_conv_params* p, cudaStream_t s) {
+  const size_t smem = kBookBytesP + 1024 + (size_t)kStagesP * (kBM * BK * 2 + pl.g.BN * BK * 2) +
+                      (size_t)kEpiWarps * 32 * kSlabPitch;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_persist_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail((int)e, "conv3d(f16): smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int total = (int)pl.grid.x;
+  const int grid = total < kNumSMs ? total : kNumSMs;
+  conv_umma_persist_kernel<BK, kHasRes><<<grid, kThreadsP, smem, s>>>(pl.map_a, pl.map_b, pl.g, total, p->scale, p->shift,
+                                                                     (const __half*)p->residual, (__half*)p->y);
+  STEP_LAUNCH_CHECK("conv_umma_persist_kernel");
+  return 0;
+}
+
 int conv3d_umma_launch(const step_conv_params* p, step_stream_t stream) {
   ConvPlan pl;
   if (int rc = build_plan(p, &pl)) return rc;
   const bool res = p->residual != nullptr;
+  // persistent kernel for 1x1x1 filters (short K loops: per-CTA setup and the epilogue dominate);
+  // one-tile-per-CTA x 2 CTAs/SM for k>1 (long K loops: two producer/MMA threads per SM keep more TMA in flight)
+  if (conv_variant() == 2 && pl.g.taps == 1) {
+    if (pl.BK == 64) return res ? launch_persist<64, true>(pl, p, cu(stream)) : launch_persist<64, false>(pl, p, cu(stream));
+    if (pl.BK == 32) return res ? launch_persist<32, true>(pl, p, cu(stream)) : launch_persist<32, false>(pl, p, cu(stream));
+    return res ? launch_persist<16, true>(pl, p, cu(stream)) : launch_persist<16, false>(pl, p, cu(stream));
+  }
   if (pl.BK == 64) return res ? launch_bk<64, true>(pl, p, cu(stream)) : launch_bk<64, false>(pl, p, cu(stream));
   if (pl.BK == 32) return res ? launch_bk<32, true>(pl, p, cu(stream)) : launch_bk<32, false>(pl, p, cu(stream));
   return res ? launch_bk<16, true>(pl, p, cu(stream)) : launch_bk<16, false>(pl, p, cu(stream));

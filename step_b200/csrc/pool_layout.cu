@@ -14,6 +14,28 @@ namespace step {
 // Mixed.branch_3, i3dpt.py:150-153, are 3x3x3 / stride 1).  Padded cells hold 0 (ConstantPad3d), cells
 // beyond the padded extent (ceil_mode overhang) are ignored.
 constexpr int kPoolCV = 4;
+template <typename T> __device__ __forceinline__ uint4 vec_lowest();
+template <> __device__ __forceinline__ uint4 vec_lowest<float>() {
+  const uint32_t v = __float_as_uint(-3.402823466e+38f);
+  return make_uint4(v, v, v, v);
+}
+template <> __device__ __forceinline__ uint4 vec_lowest<__half>() {
+  return make_uint4(0xFBFFFBFFu, 0xFBFFFBFFu, 0xFBFFFBFFu, 0xFBFFFBFFu);  // -65504 in both halves
+}
+template <typename T> __device__ __forceinline__ uint4 vec_max(uint4 a, uint4 b);
+template <> __device__ __forceinline__ uint4 vec_max<float>(uint4 a, uint4 b) {
+  return make_uint4(__float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x))),
+                    __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y))),
+                    __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z))),
+                    __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w))));
+}
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint4 vec_max<__half>(uint4 a, uint4 b) {
+  return make_uint4(hmax2_u32(a.x, b.x), hmax2_u32(a.y, b.y), hmax2_u32(a.z, b.z), hmax2_u32(a.w, b.w));
+}
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ x, int N, int T_, int H, int W, int C,
                                                         int in_ld, int KT, int KH, int KW, int ST, int SH, int SW,
@@ -34,9 +56,8 @@ __global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ x,
   for (int p = threadIdx.x / kPoolCV; p < npix; p += blockDim.x / kPoolCV) {
     const int ow = w0 + p % TW, oh = h0 + (p / TW) % TH, ot = t0 + p / (TW * TH);
     if (ow >= OW || oh >= OH || ot >= OT) continue;
-    float m[VN];
-#pragma unroll
-    for (int k = 0; k < VN; ++k) m[k] = -3.402823466e+38f;
+    // max is exact in the storage type: stay in packed half2 (4 HMNMX2 per 16-byte load, no converts)
+    uint4 m = vec_lowest<T>();
     bool touches_pad = false, any = false;
     for (int kt = 0; kt < KT; ++kt) {
       const int t = ot * ST + kt - PT;          // coordinate in the un-padded tensor
@@ -45,24 +66,72 @@ __global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ x,
       for (int kh = 0; kh < KH; ++kh) {
         const int h = oh * SH + kh - PH;
         if (h >= H + pad_hi_h) continue;
-        const bool hp = (h < 0) || (h >= H);
+        if (tp || h < 0 || h >= H) { touches_pad = true; continue; }
+        const T* rowp = x + (((size_t)n * T_ + t) * H + h) * W * in_ld + cv * VN;
         for (int kw = 0; kw < KW; ++kw) {
           const int w = ow * SW + kw - PW;
           if (w >= W + pad_hi_w) continue;
-          if (tp || hp || w < 0 || w >= W) { touches_pad = true; continue; }
-          float v[VN];
-          load16(x + ((((size_t)n * T_ + t) * H + h) * W + w) * in_ld + cv * VN, v);
-#pragma unroll
-          for (int k = 0; k < VN; ++k) m[k] = fmaxf(m[k], v[k]);
+          if (w < 0 || w >= W) { touches_pad = true; continue; }
+          m = vec_max<T>(m, *reinterpret_cast<const uint4*>(rowp + (size_t)w * in_ld));
           any = true;
         }
       }
     }
-    if (touches_pad || !any) {
+    if (touches_pad || !any) m = vec_max<T>(m, make_uint4(0, 0, 0, 0));  // +0.0 in both fp32 and fp16
+    *reinterpret_cast<uint4*>(y + ((((size_t)n * OT + ot) * OH + oh) * OW + ow) * out_ld + cv * VN) = m;
+  }
+}
+
+// 3x3x3 / stride 1 / pad 1 (Mixed.branch_3, i3dpt.py:150-153) on maps whose width is a multiple of 7
+// (112/16 .. 7): one thread produces a 7-pixel output row segment for one 16-byte channel vector.  For
+// each of the 9 (kt, kh) input rows it loads the 9 columns once (consecutive lanes = consecutive channel
+// vectors: 512 contiguous bytes per warp per load), reduces them horizontally and folds the row into the
+// 7 accumulators: ~130 instead of ~460 instructions per output vector.
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool3d_333_kernel(const T* __restrict__ x, int N, int T_, int H, int W, int C,
+                                                            int in_ld, T* __restrict__ y, int out_ld) {
+  constexpr int VN = Vec16<T>::N, WB = 7;
+  const int nvec = C / VN, wsegs = W / WB;
+  const long long total = (long long)N * T_ * H * wsegs * nvec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % nvec);
+    long long r = idx / nvec;
+    const int ws = (int)(r % wsegs); r /= wsegs;
+    const int h = (int)(r % H); r /= H;
+    const int t = (int)(r % T_);
+    const int n = (int)(r / T_);
+    const int w0 = ws * WB;
+    uint4 acc[WB];
 #pragma unroll
-      for (int k = 0; k < VN; ++k) m[k] = fmaxf(m[k], 0.0f);
+    for (int j = 0; j < WB; ++j) acc[j] = vec_lowest<T>();
+#pragma unroll
+    for (int dt = -1; dt <= 1; ++dt) {
+      const int tt = t + dt;
+      if (tt < 0 || tt >= T_) continue;
+#pragma unroll
+      for (int dh = -1; dh <= 1; ++dh) {
+        const int hh = h + dh;
+        if (hh < 0 || hh >= H) continue;
+        const T* rowp = x + ((((size_t)n * T_ + tt) * H + hh) * W + w0) * in_ld + cv * VN;
+        uint4 v[WB + 2];
+        v[0] = (w0 > 0) ? *reinterpret_cast<const uint4*>(rowp - in_ld) : vec_lowest<T>();
+#pragma unroll
+        for (int j = 0; j < WB; ++j) v[j + 1] = *reinterpret_cast<const uint4*>(rowp + (size_t)j * in_ld);
+        v[WB + 1] = (w0 + WB < W) ? *reinterpret_cast<const uint4*>(rowp + (size_t)WB * in_ld) : vec_lowest<T>();
+#pragma unroll
+        for (int j = 0; j < WB; ++j) acc[j] = vec_max<T>(acc[j], vec_max<T>(vec_max<T>(v[j], v[j + 1]), v[j + 2]));
+      }
     }
-    store16(y + ((((size_t)n * OT + ot) * OH + oh) * OW + ow) * out_ld + cv * VN, m);
+    // windows that overlap the zero padding see a 0 (ConstantPad3d, i3dpt.py:120)
+    const bool edge_th = (t == 0) || (t == T_ - 1) || (h == 0) || (h == H - 1);
+    T* orow = y + ((((size_t)n * T_ + t) * H + h) * W + w0) * out_ld + cv * VN;
+#pragma unroll
+    for (int j = 0; j < WB; ++j) {
+      uint4 m = acc[j];
+      if (edge_th || (w0 + j == 0) || (w0 + j == W - 1)) m = vec_max<T>(m, make_uint4(0, 0, 0, 0));
+      *reinterpret_cast<uint4*>(orow + (size_t)j * out_ld) = m;
+    }
   }
 }
 
@@ -262,6 +331,18 @@ extern "C" int step_maxpool3d_fwd(const void* x, int dtype, int N, int T, int H,
   STEP_CHECK_ARG(x && y && N > 0 && T > 0 && H > 0 && W > 0, "maxpool3d: bad shape/pointer");
   STEP_CHECK_ARG(C % vn == 0 && in_ld % vn == 0 && out_ld % vn == 0, "maxpool3d: C/ld must be multiples of %d", vn);
   STEP_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "maxpool3d: pointers must be 16-byte aligned");
+  if (KT == 3 && KH == 3 && KW == 3 && ST == 1 && SH == 1 && SW == 1 && PT == 1 && PH == 1 && PW == 1 && pad_hi_t == 1 &&
+      pad_hi_h == 1 && pad_hi_w == 1 && OT == T && OH == H && OW == W && W % 7 == 0) {
+    long long total = (long long)N * T * H * (W / 7) * (C / vn);
+    if (dtype == STEP_F16)
+      maxpool3d_333_kernel<__half><<<grid_for(total, 256), 256, 0, cu(stream)>>>((const __half*)x, N, T, H, W, C, in_ld,
+                                                                                 (__half*)y, out_ld);
+    else
+      maxpool3d_333_kernel<float><<<grid_for(total, 256), 256, 0, cu(stream)>>>((const float*)x, N, T, H, W, C, in_ld,
+                                                                                (float*)y, out_ld);
+    STEP_LAUNCH_CHECK("maxpool3d_333_kernel");
+    return 0;
+  }
   // tile: up to 4 x 8 x 8 output pixels (whole rows on the small maps), 64-byte channel chunks
   const int TW = OW < 8 ? OW : (OW % 7 == 0 ? 7 : 8), TH = OH < 8 ? OH : (OH % 7 == 0 ? 7 : 8), TT = OT < 4 ? OT : 4;
   long long tiles = (long long)N * ceil_div(OT, TT) * ceil_div(OH, TH) * ceil_div(OW, TW);

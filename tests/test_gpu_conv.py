@@ -226,3 +226,31 @@ def test_stem_s2d_fp16_vs_fp32_simt():
     torch.cuda.synchronize()
     err = float((outs[0] - outs[1]).abs().max())
     assert err <= 2e-2 * float(outs[1].abs().max()), err
+
+
+POOL_CASES = [
+    # N, T, H, W, C, k, s
+    (2, 4, 7, 7, 64, (3, 3, 3), (1, 1, 1)),      # specialised 3x3x3 kernel (W % 7 == 0)
+    (1, 3, 14, 28, 32, (3, 3, 3), (1, 1, 1)),
+    (1, 4, 9, 10, 16, (3, 3, 3), (1, 1, 1)),     # generic kernel
+    (1, 4, 12, 14, 24, (1, 3, 3), (1, 2, 2)),
+    (2, 5, 13, 25, 8, (3, 3, 3), (2, 2, 2)),     # odd sizes: ceil_mode overhang + TF padding
+    (1, 2, 25, 25, 16, (1, 3, 3), (1, 2, 2)),    # the ContextNet pool at 400x400 (25 -> 13)
+]
+
+
+@pytest.mark.parametrize("code", [L.F32, L.F16], ids=["fp32", "fp16"])
+@pytest.mark.parametrize("case", POOL_CASES)
+def test_maxpool_tf_padding_matches_torch(case, code):
+    N, T, H, W, C, k, s = case
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, T, H, W, C, generator=g)          # negative values exercise the zero padding
+    xd = x.to(E.torch_dtype(code)).cuda()
+    out = E.maxpool(Act(xd), k, s)
+    torch.cuda.synchronize()
+    xr = xd.float().cpu().permute(0, 4, 1, 2, 3)
+    pads = [E.same_pad(k[i], s[i]) for i in range(3)]
+    xr = F.pad(xr, (pads[2][0], pads[2][1], pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
+    ref = F.max_pool3d(xr, k, s, ceil_mode=True).permute(0, 2, 3, 4, 1)
+    assert tuple(out.buf.shape) == tuple(ref.shape)
+    assert torch.equal(out.buf.float().cpu(), ref)        # max is exact in either storage type
