@@ -148,6 +148,15 @@ typedef struct {
   int res_ld, res_coff;
   void* y;
   int a_mode;                /* f16 path: 0 auto, 1 linear (1x1x1 only), 2 box tiles, 3 TMA im2col */
+  /* Horizontally fused 1x1x1 layers that share an input (Mixed.branch_0 / branch_1[0] / branch_2[0],
+   * i3dpt.py:133-147): output channels [0, split[0]) go to y, [split[0], split[1]) to y_extra[0],
+   * [split[1], Cout) to y_extra[1], each with its own channel stride / offset.  n_splits = 0: plain conv.
+   * f16 1x1x1 only; split points must be multiples of 16. */
+  int n_splits;
+  int split[2];
+  void* y_extra[2];
+  int ld_extra[2];
+  int coff_extra[2];
 } step_conv_params;
 int step_conv3d_fwd(const step_conv_params* p, step_stream_t stream);
 

@@ -40,8 +40,10 @@ extern "C" int step_conv3d_fwd(const step_conv_params* p, step_stream_t stream) 
   STEP_CHECK_ARG(p->N > 0 && p->T > 0 && p->H > 0 && p->W > 0 && p->Cin > 0 && p->Cout > 0, "conv3d: bad extent");
   STEP_CHECK_ARG(p->KT > 0 && p->KH > 0 && p->KW > 0 && p->ST > 0 && p->SH > 0 && p->SW > 0, "conv3d: bad filter/stride");
   STEP_CHECK_ARG(p->OT > 0 && p->OH > 0 && p->OW > 0, "conv3d: bad output extent");
-  STEP_CHECK_ARG(p->out_ld >= p->out_coff + p->Cout, "conv3d: output slice [%d,%d) exceeds out_ld %d", p->out_coff,
-                 p->out_coff + p->Cout, p->out_ld);
+  STEP_CHECK_ARG(p->n_splits >= 0 && p->n_splits <= 2, "conv3d: bad n_splits");
+  STEP_CHECK_ARG(p->n_splits > 0 || p->out_ld >= p->out_coff + p->Cout, "conv3d: output slice [%d,%d) exceeds out_ld %d",
+                 p->out_coff, p->out_coff + p->Cout, p->out_ld);
+  STEP_CHECK_ARG(p->n_splits == 0 || (p->dtype == STEP_F16 && p->a_mode != 9), "conv3d: fused outputs are f16 tensor-core only");
   // every output position must only need taps that the declared low padding makes reachable
   STEP_CHECK_ARG((p->OT - 1) * p->ST - p->PT < p->T && (p->OH - 1) * p->SH - p->PH < p->H && (p->OW - 1) * p->SW - p->PW < p->W,
                  "conv3d: output extent inconsistent with input/stride/pad");

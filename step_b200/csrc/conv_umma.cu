@@ -42,6 +42,9 @@ struct ConvGeom {
   int kblocks_per_tap;          // ceil(Cin / BK)
   int BN, n_tiles;              // N tile (multiple of 16) and count
   int n_stages;                 // smem pipeline depth used by the one-tile-per-CTA kernel
+  int n_stages_p, slab_pitch;   // persistent kernel: pipeline depth, bytes per staged output row (odd multiple of 16)
+  int n_splits, split[2], ld_extra[2], coff_extra[2];  // fused 1x1x1 layers: extra destinations by column range
+  __half* y_extra[2];
   int Cout, out_ld, out_coff, res_ld, res_coff, relu;
   int OT, OH, OW, Nimg;
   long long M;                  // Nimg*OT*OH*OW
@@ -341,9 +344,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 constexpr int kStagesP = 5;
 constexpr int kEpiWarps = 8;                       // (lane quarter) x (column half)
 constexpr int kThreadsP = 64 + kEpiWarps * 32;     // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
-constexpr int kMaxBNP = 128;                       // the persistent kernel keeps 2 x 128-column accumulators
+constexpr int kMaxBNP = 256;                       // the persistent kernel keeps 2 x BN-column accumulators (all 512 TMEM columns)
 constexpr int kSlabCols = kMaxBNP / 2;             // columns one epilogue warp handles per tile
-constexpr int kSlabPitch = kSlabCols * 2 + 16;     // bytes, odd multiple of 16 -> conflict-free 16B stores
 constexpr int kBookBytesP = 4096 + 8 * 2 * kSlabCols * 4;  // barriers etc. (first 4 KB) + per-warp scale/shift
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -386,8 +388,9 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + kBookBytesP + 1023) & ~(uintptr_t)1023);
   const int b_bytes = g.BN * BK * 2;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStagesP * kABytes;
-  uint8_t* slabs = sB + kStagesP * b_bytes;     // [kEpiWarps][32 rows][kSlabPitch]
+  uint8_t* sB = smem + g.n_stages_p * kABytes;
+  uint8_t* slabs = sB + g.n_stages_p * b_bytes;  // [kEpiWarps][32 rows][slab_pitch]
+  const int kSlabPitch = g.slab_pitch;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = g.taps * g.kblocks_per_tap;
@@ -441,7 +444,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
               tma_load_im2col_5d(&map_a, &full_bar[stage], a_dst, c0, iw, ih, it, in_, (uint16_t)kw, (uint16_t)kh, (uint16_t)kt);
             }
             tma_load_3d(&map_b, &full_bar[stage], b_dst, c0, tap, o.n0);
-            if (++stage == kStagesP) { stage = 0; phase ^= 1; }
+            if (++stage == g.n_stages_p) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -469,7 +472,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           if (kb == num_kb - 1) umma_commit(&tfull_bar[buf]);
         }
         __syncwarp();
-        if (++stage == kStagesP) { stage = 0; phase ^= 1; }
+        if (++stage == g.n_stages_p) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -486,35 +489,46 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     uint8_t* slab = slabs + (size_t)ew * 32 * kSlabPitch;
     uint8_t* srow = slab + (size_t)lane * kSlabPitch;
     const int row = lane_grp * 32 + lane;
+    // row -> output pixel of a tile
+    auto row_pixel = [&](const TileOrigin& o) -> long long {
+      if (g.mode == A_BOX) {
+        int dw = row % g.bw, r = row / g.bw;
+        int dh = r % g.bh, dt = r / g.bh;
+        int ow = o.bw0 + dw, oh = o.bh0 + dh, ot = o.bt0 + dt;
+        if (dt < g.bt && ow < g.OW && oh < g.OH && ot < g.OT) return (((long long)o.bn * g.OT + ot) * g.OH + oh) * g.OW + ow;
+        return -1;
+      }
+      long long m = o.m0 + row;
+      return m < g.M ? m : -1;
+    };
+    // Residual rows (two_branch.py:79-81) are row-strided 16-byte loads: they are issued for tile i+1 right
+    // after tile i's accumulator has been drained, so their latency hides behind the copy-out of tile i
+    // and the MMAs of tile i+1 instead of stalling the epilogue.
+    uint4 rreg[kSlabCols / 8];
+    auto prefetch_residual = [&](int tile) {
+      if (!kHasRes || tile >= total_tiles) return;
+      const TileOrigin o = tile_origin(g, tile);
+      const long long px = row_pixel(o);
+      const int nb = o.n0 + col0;
+      const __half* rrow = residual + (px < 0 ? 0 : (size_t)px * g.res_ld + g.res_coff + nb);
+#pragma unroll
+      for (int j = 0; j < kSlabCols / 8; ++j) {
+        rreg[j] = make_uint4(0, 0, 0, 0);
+        if (px >= 0 && j * 8 < ncol && nb + j * 8 < g.Cout) rreg[j] = *reinterpret_cast<const uint4*>(rrow + j * 8);
+      }
+    };
+    prefetch_residual(blockIdx.x);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
       const TileOrigin o = tile_origin(g, tile);
-      long long pix = -1;
-      if (g.mode == A_BOX) {
-        int dw = row % g.bw, r = row / g.bw;
-        int dh = r % g.bh, dt = r / g.bh;
-        int ow = o.bw0 + dw, oh = o.bh0 + dh, ot = o.bt0 + dt;
-        if (dt < g.bt && ow < g.OW && oh < g.OH && ot < g.OT) pix = (((long long)o.bn * g.OT + ot) * g.OH + oh) * g.OW + ow;
-      } else {
-        long long m = o.m0 + row;
-        if (m < g.M) pix = m;
-      }
+      const long long pix = row_pixel(o);
       const int nbase = o.n0 + col0;               // first output channel this warp handles
       for (int i = lane; i < ncol; i += 32) {
         const int c = nbase + i;
         s_scale[i] = (scale && c < g.Cout) ? scale[c] : 1.0f;
         s_shift[i] = (shift && c < g.Cout) ? shift[c] : 0.0f;
-      }
-      uint4 rreg[kSlabCols / 8];
-      if (kHasRes) {
-        const __half* rrow = residual + (pix < 0 ? 0 : (size_t)pix * g.res_ld + g.res_coff + nbase);
-#pragma unroll
-        for (int j = 0; j < kSlabCols / 8; ++j) {
-          rreg[j] = make_uint4(0, 0, 0, 0);
-          if (pix >= 0 && j * 8 < ncol && nbase + j * 8 < g.Cout) rreg[j] = *reinterpret_cast<const uint4*>(rrow + j * 8);
-        }
       }
       __syncwarp();
       mbar_wait(&tfull_bar[buf], tphase);
@@ -552,14 +566,21 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      prefetch_residual(tile + gridDim.x);
       // coalesced copy-out of this warp's 32 x ncol slab
       const int cpr = ncol >> 3;
       for (int i = lane; i < 32 * cpr; i += 32) {
         const int rr = i / cpr, ch = i - rr * cpr;
         const long long rp = __shfl_sync(0xffffffffu, pix, rr);
-        if (rp >= 0 && nbase + ch * 8 < g.Cout) {
+        const int col = nbase + ch * 8;
+        if (rp >= 0 && col < g.Cout) {
           uint4 val = *reinterpret_cast<const uint4*>(slab + (size_t)rr * kSlabPitch + ch * 16);
-          *reinterpret_cast<uint4*>(y + (size_t)rp * g.out_ld + g.out_coff + nbase + ch * 8) = val;
+          __half* dst = y + (size_t)rp * g.out_ld + g.out_coff + col;
+          if (g.n_splits > 0 && col >= g.split[0]) {
+            const int d = (g.n_splits > 1 && col >= g.split[1]) ? 1 : 0;
+            dst = g.y_extra[d] + (size_t)rp * g.ld_extra[d] + g.coff_extra[d] + (col - g.split[d]);
+          }
+          *reinterpret_cast<uint4*>(dst) = val;
         }
       }
       __syncwarp();
@@ -704,13 +725,30 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   {
     // N tile: as wide as the accumulator allows -- every N tile re-reads the whole A operand through L2,
     // which is what bounds the k>1 layers.  Residual layers and the persistent (1x1) variant stay <= 128.
-    const int cap = (p->residual || (taps == 1 && conv_variant() == 2)) ? kMaxBNRes : kMaxBN;
+    const bool persist = taps == 1 && conv_variant() == 2;
+    const int cap = persist ? kMaxBNP : (p->residual ? kMaxBNRes : kMaxBN);
     g.n_tiles = (p->Cout + cap - 1) / cap;
     g.BN = (((p->Cout + g.n_tiles - 1) / g.n_tiles) + 15) / 16 * 16;
     g.n_stages = g.BN > 128 ? 2 : 3;
+    g.n_stages_p = g.BN > 128 ? 3 : 5;
+    g.slab_pitch = (((g.BN >> 4) + 1) / 2) * 16 * 2 + 16;
   }
   g.Cout = p->Cout; g.out_ld = p->out_ld; g.out_coff = p->out_coff; g.res_ld = p->res_ld; g.res_coff = p->res_coff;
   g.relu = p->relu;
+  g.n_splits = p->n_splits;
+  if (p->n_splits) {
+    STEP_CHECK_ARG(p->n_splits >= 1 && p->n_splits <= 2 && taps == 1 && conv_variant() == 2 && !p->residual,
+                   "conv3d(f16): fused outputs need a 1x1x1 filter (persistent kernel), no residual, 1-2 splits");
+    int prev = 0;
+    for (int i = 0; i < p->n_splits; ++i) {
+      STEP_CHECK_ARG(p->split[i] % 16 == 0 && p->split[i] > prev && p->split[i] < p->Cout && p->y_extra[i] &&
+                     p->ld_extra[i] % 8 == 0 && p->coff_extra[i] % 8 == 0 && ((uintptr_t)p->y_extra[i] & 15) == 0,
+                     "conv3d(f16): bad split %d", i);
+      prev = p->split[i];
+      g.split[i] = p->split[i]; g.y_extra[i] = (__half*)p->y_extra[i]; g.ld_extra[i] = p->ld_extra[i]; g.coff_extra[i] = p->coff_extra[i];
+    }
+    STEP_CHECK_ARG(p->out_ld >= p->out_coff + p->split[0], "conv3d(f16): first destination too narrow");
+  }
   g.OT = p->OT; g.OH = p->OH; g.OW = p->OW; g.Nimg = p->N;
   g.M = (long long)p->N * p->OT * p->OH * p->OW;
   g.idesc = (1u << 4) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);  // f16 x f16 -> f32, K-major A/B
@@ -799,8 +837,8 @@ static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t
 
 template <int BK, bool kHasRes>
 static int launch_persist(const ConvPlan& pl, const step_conv_params* p, cudaStream_t s) {
-  const size_t smem = kBookBytesP + 1024 + (size_t)kStagesP * (kBM * BK * 2 + pl.g.BN * BK * 2) +
-                      (size_t)kEpiWarps * 32 * kSlabPitch;
+  const size_t smem = kBookBytesP + 1024 + (size_t)pl.g.n_stages_p * (kBM * BK * 2 + pl.g.BN * BK * 2) +
+                      (size_t)kEpiWarps * 32 * pl.g.slab_pitch;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_persist_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -20,6 +20,45 @@ A_MODE = {"box": L.A_BOX, "im2col": L.A_IM2COL, "auto": L.A_AUTO, "simt": L.A_SI
 RECORDER = None
 
 
+# Independent branches of an Inception block (models/i3dpt.py:157-163 runs them serially) are issued on
+# side streams: at these shapes one branch often has < 148 tiles, so overlapping the four branches is what
+# fills the SMs.  Under CUDA-graph capture the fork/join events become graph edges.
+BRANCH_STREAMS = os.environ.get("STEP_B200_BRANCH_STREAMS", "1") != "0"
+FUSE_1X1 = os.environ.get("STEP_B200_FUSE_1X1", "1") != "0"
+_side_streams = {}
+
+
+def side_streams(device, n=3):
+    key = (device.type, device.index)
+    st = _side_streams.get(key)
+    if st is None or len(st) < n:
+        st = [torch.cuda.Stream(device=device) for _ in range(n)]
+        _side_streams[key] = st
+    return st[:n]
+
+
+def run_parallel(device, main_fn, side_fns, first_side=0):
+    """Run main_fn on the current stream and each side_fn on its own side stream; join before returning.
+    first_side: index of the first side stream to use (nested calls must not share a stream)."""
+    if not BRANCH_STREAMS or not side_fns:
+        main_fn()
+        for f in side_fns:
+            f()
+        return
+    cur = torch.cuda.current_stream(device)
+    fork = cur.record_event()
+    streams = side_streams(device, first_side + len(side_fns))[first_side:]
+    joins = []
+    for st, f in zip(streams, side_fns):
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            f()
+            joins.append(st.record_event())
+    main_fn()
+    for ev in joins:
+        cur.wait_event(ev)
+
+
 def torch_dtype(code):
     return torch.float16 if code == L.F16 else torch.float32
 
@@ -118,8 +157,10 @@ def params_key(*tensors):
 
 
 def conv(x, w_packed, scale, shift, out, k, stride=(1, 1, 1), pad_lo=None, relu=True, residual=None,
-         a_mode=None, out_dims=None):
-    """Launch step_conv3d_fwd: x (Act) * w_packed [Cout, taps, w_ld] -> out (Act slice)."""
+         a_mode=None, out_dims=None, extra_outs=None):
+    """Launch step_conv3d_fwd: x (Act) * w_packed [Cout, taps, w_ld] -> out (Act slice).
+    extra_outs: up to two more Act slices; output channels are then split [out.C | extra[0].C | extra[1].C]
+    (horizontally fused 1x1x1 layers sharing the input)."""
     code = x.code
     if pad_lo is None:
         pad_lo = tuple(same_pad(k[i], stride[i])[0] for i in range(3))
@@ -129,7 +170,15 @@ def conv(x, w_packed, scale, shift, out, k, stride=(1, 1, 1), pad_lo=None, relu=
     p.dtype = code
     p.N, p.T, p.H, p.W = x.N, x.T, x.H, x.W
     p.Cin, p.in_ld = x.C, x.ld
-    p.Cout, p.out_ld, p.out_coff = out.C, out.ld, out.coff
+    p.Cout, p.out_ld, p.out_coff = out.C + sum(e.C for e in (extra_outs or [])), out.ld, out.coff
+    if extra_outs:
+        p.n_splits = len(extra_outs)
+        edge = out.C
+        for i, e in enumerate(extra_outs):
+            p.split[i] = edge
+            p.y_extra[i] = e.buf.data_ptr()
+            p.ld_extra[i], p.coff_extra[i] = e.ld, e.coff
+            edge += e.C
     p.KT, p.KH, p.KW = k
     p.ST, p.SH, p.SW = stride
     p.PT, p.PH, p.PW = pad_lo
@@ -150,7 +199,8 @@ def conv(x, w_packed, scale, shift, out, k, stride=(1, 1, 1), pad_lo=None, relu=
     assert (out.N, out.T, out.H, out.W) == (x.N,) + tuple(out_dims), "conv: output buffer shape mismatch"
     L.check(L.lib().step_conv3d_fwd(p, L.stream()))
     if RECORDER is not None:
-        RECORDER.append((p, (x.buf, w_packed, scale, shift, out.buf, residual.buf if residual is not None else None)))
+        RECORDER.append((p, (x.buf, w_packed, scale, shift, out.buf, residual.buf if residual is not None else None,
+                             [e.buf for e in (extra_outs or [])])))
     return out
 
 

@@ -112,10 +112,52 @@ class Mixed(torch.nn.Module):
         c0, c1, c2, c3 = self.out_plan
         if out is None:
             out = Act.empty(x.N, x.T, x.H, x.W, c0 + c1 + c2 + c3, x.code, x.device)
-        self.branch_0(x, out=out.slice(0, c0))
-        self.branch_1[1](self.branch_1[0](x), out=out.slice(c0, c1))
-        self.branch_2[1](self.branch_2[0](x), out=out.slice(c0 + c1, c2))
-        self.branch_3[1](self.branch_3[0](x), out=out.slice(c0 + c1 + c2, c3))
+        if x.code == L.F16 and E.FUSE_1X1:
+            return self._forward_fused(x, out)
+        # the heaviest branch (1x1 -> 3x3x3) stays on the caller's stream, the other three fork off
+        E.run_parallel(
+            x.device,
+            lambda: self.branch_1[1](self.branch_1[0](x), out=out.slice(c0, c1)),
+            [lambda: self.branch_0(x, out=out.slice(0, c0)),
+             lambda: self.branch_2[1](self.branch_2[0](x), out=out.slice(c0 + c1, c2)),
+             lambda: self.branch_3[1](self.branch_3[0](x), out=out.slice(c0 + c1 + c2, c3))])
+        return out
+
+
+    def _fused_weights(self):
+        """branch_0 | branch_1[0] | branch_2[0] read the same input (i3dpt.py:133-147): one GEMM with
+        N = o0 + o1 + o3 whose epilogue scatters the three column ranges to their destinations."""
+        units = (self.branch_0, self.branch_1[0], self.branch_2[0])
+        parts = [u.packed(L.F16) for u in units]
+        key = tuple(id(p[0]) for p in parts)
+        c = self.__dict__.get("_fused")
+        if c is None or c[0] != key:
+            w = torch.cat([p[0] for p in parts], 0).contiguous()
+            scale = torch.cat([p[1] for p in parts]).contiguous()
+            shift = torch.cat([p[2] for p in parts]).contiguous()
+            self.__dict__["_fused"] = (key, (w, scale, shift))
+            c = self.__dict__["_fused"]
+        return c[1]
+
+    def _forward_fused(self, x, out):
+        c0, c1, c2, c3 = self.out_plan
+        w, scale, shift = self._fused_weights()
+        m1 = self.branch_1[0].conv3d.out_channels
+        m2 = self.branch_2[0].conv3d.out_channels
+        t1 = Act.empty(x.N, x.T, x.H, x.W, m1, x.code, x.device)
+        t2 = Act.empty(x.N, x.T, x.H, x.W, m2, x.code, x.device)
+
+        def trunk():
+            E.conv(x, w, scale, shift, out.slice(0, c0), (1, 1, 1), extra_outs=[t1, t2])
+
+        def tail():
+            E.run_parallel(x.device,
+                           lambda: self.branch_1[1](t1, out=out.slice(c0, c1)),
+                           [lambda: self.branch_2[1](t2, out=out.slice(c0 + c1, c2))])
+        # the pool -> 1x1 branch only needs x: it overlaps the fused GEMM and the 3x3x3 convs
+        E.run_parallel(x.device, lambda: (trunk(), tail()),
+                       [lambda: self.branch_3[1](self.branch_3[0](x), out=out.slice(c0 + c1 + c2, c3))],
+                       first_side=2)
         return out
 
 

@@ -112,10 +112,12 @@ class Bottleneck_resample(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        res = conv2d(self.conv1, x, False)
-        o = conv2d(self.conv2, x, True)
-        o = conv2d(self.conv3, o, True)
-        return conv2d(self.conv4, o, True, residual=res)
+        box = {}
+        # the residual projection (conv1) is independent of the conv2 -> conv3 chain
+        E.run_parallel(x.device,
+                       lambda: box.__setitem__("o", conv2d(self.conv3, conv2d(self.conv2, x, True), True)),
+                       [lambda: box.__setitem__("res", conv2d(self.conv1, x, False))])
+        return conv2d(self.conv4, box["o"], True, residual=box["res"])
 
 
 class ContextNet(nn.Module):

@@ -254,3 +254,31 @@ def test_maxpool_tf_padding_matches_torch(case, code):
     ref = F.max_pool3d(xr, k, s, ceil_mode=True).permute(0, 2, 3, 4, 1)
     assert tuple(out.buf.shape) == tuple(ref.shape)
     assert torch.equal(out.buf.float().cpu(), ref)        # max is exact in either storage type
+
+
+def test_fused_1x1_multi_destination_matches_separate_convs():
+    """Mixed's three 1x1x1 branches as one GEMM whose epilogue scatters column ranges (i3dpt.py:133-147)."""
+    g = torch.Generator().manual_seed(11)
+    N, T, H, W, Cin = 2, 4, 7, 7, 832
+    outs = (256, 160, 32)
+    x = torch.randn(N, T, H, W, Cin, generator=g).half().cuda()
+    ws = [(torch.randn(c, Cin, 1, 1, 1, generator=g) / Cin ** 0.5).half() for c in outs]
+    scale = (torch.rand(sum(outs), generator=g) + 0.5).cuda()
+    shift = torch.randn(sum(outs), generator=g).cuda()
+    xa = Act(x.contiguous())
+    wp = torch.cat([E.pack_conv_weight(w.cuda(), L.F16) for w in ws], 0).contiguous()
+    big = torch.zeros((N, T, H, W, 512), dtype=torch.float16, device="cuda")       # branch_0 lands in a slice
+    t1 = torch.zeros((N, T, H, W, outs[1]), dtype=torch.float16, device="cuda")
+    t2 = torch.zeros((N, T, H, W, outs[2] + 8), dtype=torch.float16, device="cuda")
+    E.conv(xa, wp, scale, shift, Act(big, outs[0], 64), (1, 1, 1), extra_outs=[Act(t1), Act(t2, outs[2], 8)])
+    torch.cuda.synchronize()
+    off = 0
+    for w, dst in zip(ws, (big[..., 64:64 + outs[0]], t1, t2[..., 8:])):
+        c = w.shape[0]
+        ref = run_conv(x, w, L.F16, (1, 1, 1), (1, 1, 1), scale[off:off + c].contiguous(), shift[off:off + c].contiguous(),
+                       True, None, L.A_SIMT).float()
+        err = float((dst.float() - ref).abs().max())
+        assert err <= 2e-3 * float(ref.abs().max()) + 2e-3, (c, err)
+        off += c
+    assert float(big[..., :64].abs().max()) == 0 and float(big[..., 64 + outs[0]:].abs().max()) == 0
+    assert float(t2[..., :8].abs().max()) == 0
