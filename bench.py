@@ -138,17 +138,37 @@ def run_ours(args):
     launches_per_step = _lib.launch_count() - l_before
     del cf0
     # the public fast path: the whole step captured once into a CUDA graph (step_b200/runner.py)
-    runner = step_b200.StepRunner(cfg, nets, B, W["T_in"], W["HW"], W["HW"], tubes, device=dev,
-                                  use_graph=not args.no_graph)
+    # args.inflight independent batches are kept in flight on separate streams (double buffering):
+    # the H2D copy / small-grid layers of one batch overlap the other batch's kernels.
+    n_run = max(1, args.inflight)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_run)]
+    runners = []
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(st):
+            runners.append(step_b200.StepRunner(cfg, nets, B, W["T_in"], W["HW"], W["HW"], tubes, device=dev,
+                                                use_graph=not args.no_graph))
+    torch.cuda.synchronize()
+    turn = [0]
 
     def step(x):
-        last = runner(x)[-1]
+        i = turn[0] % n_run
+        turn[0] += 1
+        cur = torch.cuda.current_stream(dev)
+        streams[i].wait_stream(cur)
+        with torch.cuda.stream(streams[i]):
+            last = runners[i](x)[-1]
+        step.last_stream = streams[i]
+        if n_run == 1:
+            cur.wait_stream(streams[i])
         if gather is not None:  # one NCCL all_gather of the fixed-shape detections per batch
-            det = torch.cat([last["pred_prob"][:, 0], last["pred_loc"][:, cfg.T // 2]], dim=1).contiguous()
-            dist.all_gather_into_tensor(gather.view(-1, det.shape[1]), det)
+            with torch.cuda.stream(streams[i]):
+                det = torch.cat([last["pred_prob"][:, 0], last["pred_loc"][:, cfg.T // 2]], dim=1).contiguous()
+                dist.all_gather_into_tensor(gather.view(-1, det.shape[1]), det)
         return last
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -159,6 +179,9 @@ def run_ours(args):
         e0.record()
         for _ in range(steps):
             fn()
+        cur = torch.cuda.current_stream(dev)
+        for st in streams:      # the timed region ends when every in-flight batch has finished
+            cur.wait_stream(st)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -166,12 +189,21 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    host_out = [{"p": torch.empty_like(out_host["p"]).pin_memory(), "l": torch.empty_like(out_host["l"]).pin_memory()}
+                for _ in range(n_run)]
+    pending = [None] * n_run
+
     def e2e_step():
-        x = clips_host.to(dev, non_blocking=True)
-        last = step(x)
-        out_host["p"].copy_(last["pred_prob"][:, 0], non_blocking=True)
-        out_host["l"].copy_(last["pred_loc"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the detections every batch
+        # public API with host buffers: H2D of the batch (pinned, async on the batch's stream), the step, D2H of
+        # the detections; the caller consumes batch i's detections before re-using its slot (one event wait).
+        i = turn[0] % n_run
+        if pending[i] is not None:
+            pending[i].synchronize()
+        last = step(clips_host)       # StepRunner copies the pinned host batch into its static input
+        with torch.cuda.stream(streams[i]):
+            host_out[i]["p"].copy_(last["pred_prob"][:, 0], non_blocking=True)
+            host_out[i]["l"].copy_(last["pred_loc"], non_blocking=True)
+            pending[i] = streams[i].record_event()
 
     for _ in range(args.warmup):
         step(clips_dev)
@@ -230,7 +262,8 @@ def run_ours(args):
         "config": {"workload": "C4: full STEP inference, two_branch, 11 proposals, max_iter=3, batch 8/GPU, "
                                "T=32, 224x224 (BASELINE.json configs[3])", "batch_per_gpu": B,
                    "global_batch": B * world, "proposals": W["N"], "l2": "inputs+activations > L2 (batch = 154 MB fp32)",
-                   "a_mode": os.environ.get("STEP_B200_AMODE", "box"), "cuda_graph": not args.no_graph,
+                   "a_mode": os.environ.get("STEP_B200_AMODE", "im2col"), "cuda_graph": not args.no_graph,
+                   "batches_in_flight": n_run,
                    "parallelism": "clip-parallel x%d" % world},
         "e2e": {"value": round(total_clips / (ms_e2e * 1e-3), 3), "unit": "clips/s",
                 "h2d_bytes_per_step": int(clips_host.numel() * 4),
@@ -323,6 +356,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying the CUDA graph")
+    ap.add_argument("--inflight", type=int, default=2, help="independent batches kept in flight on separate streams")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

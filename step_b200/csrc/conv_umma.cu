@@ -664,7 +664,7 @@ static int pick_bk(int Cin) {
   const int cands[3] = {64, 32, 16};
   for (int i = 0; i < 3; ++i) {
     int bk = cands[i];
-    long cost = (long)((Cin + bk - 1) / bk) * (bk + 16);
+    long cost = (long)((Cin + bk - 1) / bk) * (bk + 8);  // padded K plus a per-k-block overhead term
     if (best_cost < 0 || cost < best_cost) { best = bk; best_cost = cost; }
   }
   return best;

@@ -10,9 +10,10 @@ import torch
 from . import _lib as L
 
 # Addressing mode of the fp16 implicit-GEMM for filters larger than 1x1x1 (include/step_b200.h a_mode):
-# "box" = tiled TMA boxes with zero-filled halo, "im2col" = TMA im2col mode (dense M tiles).
+# "box" = tiled TMA boxes with zero-filled halo, "im2col" = TMA im2col mode (dense M tiles; default, both are
+# validated byte-for-byte by tests/test_gpu_conv.py::test_tma_tile_addressing).
 A_MODE = {"box": L.A_BOX, "im2col": L.A_IM2COL, "auto": L.A_AUTO, "simt": L.A_SIMT}[
-    os.environ.get("STEP_B200_AMODE", "box")]
+    os.environ.get("STEP_B200_AMODE", "im2col")]
 
 
 # When set to a list, conv() appends (params, tensors-kept-alive) for every launch: bench.py replays
@@ -24,7 +25,7 @@ RECORDER = None
 # side streams: at these shapes one branch often has < 148 tiles, so overlapping the four branches is what
 # fills the SMs.  Under CUDA-graph capture the fork/join events become graph edges.
 BRANCH_STREAMS = os.environ.get("STEP_B200_BRANCH_STREAMS", "1") != "0"
-FUSE_1X1 = os.environ.get("STEP_B200_FUSE_1X1", "1") != "0"
+FUSE_1X1 = os.environ.get("STEP_B200_FUSE_1X1", "1") != "0" and os.environ.get("STEP_B200_CONV", "2") != "1"
 _side_streams = {}
 
 

@@ -5,6 +5,6 @@ run() { name=$1; shift; echo "=== $name" ; timeout 900 "$@" > gpurun_out/$name.l
 export STEP_B200_AMODE=${AMODE:-im2col}
 run x1_tests   python -m pytest tests -q -m gpu --tb=short -x
 run x2_bench   python bench.py --steps 10 --warmup 3 --skip-cpu
-STEP_B200_CONV=1 run x2b_bench_v1 python bench.py --steps 10 --warmup 3 --skip-cpu
-run x3_launches ncu --kernel-name-base demangled -k regex:step:: --metrics gpu__time_duration.sum --clock-control none -s 320 -c 170 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 1 --warmup 3 --skip-cpu --no-graph
+run x2b_bench_1flight python bench.py --steps 10 --warmup 3 --skip-cpu --inflight 1
+run x3_launches ncu --kernel-name-base demangled -k regex:step:: --metrics gpu__time_duration.sum --clock-control none -s 300 -c 300 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 1 --warmup 3 --skip-cpu --no-graph
 python tools/launch_summary.py gpurun_out/launches_r1.csv | head -16
