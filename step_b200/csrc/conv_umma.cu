@@ -42,7 +42,7 @@ struct ConvGeom {
   int kblocks_per_tap;          // ceil(Cin / BK)
   int BN, n_tiles;              // N tile (multiple of 16) and count
   int n_stages;                 // smem pipeline depth used by the one-tile-per-CTA kernel
-  int n_stages_p, slab_pitch;   // persistent kernel: pipeline depth, bytes per staged output row (odd multiple of 16)
+  int n_stages_p, mh, tmem_bufs;  // persistent kernel: pipeline depth, 128-row halves per tile, accumulator sets
   int n_splits, split[2], ld_extra[2], coff_extra[2];  // fused 1x1x1 layers: extra destinations by column range
   __half* y_extra[2];
   int Cout, out_ld, out_coff, res_ld, res_coff, relu;
@@ -336,38 +336,45 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ---- persistent variant ----------------------------------------------------------------------
-// One CTA per SM loops over output tiles.  Three overlapped pipelines: smem stages (TMA <-> MMA),
-// two TMEM accumulators (MMA <-> epilogue: the MMA warp starts tile i+1 while the epilogue drains
-// tile i), and per-warp epilogue staging slabs.  TMEM allocation, barrier setup and descriptor
-// prefetch are paid once per CTA instead of once per tile, which is what the many small-K layers of
-// the network (1x1x1 branches, the 256->1024 bottleneck outputs) were bound by.
-constexpr int kStagesP = 5;
-constexpr int kEpiWarps = 8;                       // (lane quarter) x (column half)
+// One CTA per SM loops over output tiles of (mh x 128) rows x BN columns, mh in {1, 2}.
+//
+// Why this shape (ncu, profiles/): with 128 x BN tiles the tensor pipe sat at 50-60 % while L2 ran at
+// ~40 % -- the kernel was bound by the latency x bandwidth product: at full MMA rate a 128 x 160 tile needs
+// 112 B/clk of operands per SM, i.e. > 200 KB in flight to cover ~1 us of L2/TMA latency, more than an SM has
+// shared memory for.  Two 128-row halves that share the B (weight) tile cut the operand bytes per MMA
+// cycle by ~1/3 (the weights of a conv are re-read by every M tile and are as much traffic as the
+// activations), and one CTA per SM lets the pipeline use all ~200 KB of shared memory for stages.
+//
+// Pipelines: smem stages (TMA <-> MMA), TMEM accumulators (MMA <-> epilogue; double-buffered when
+// mh * BN <= 256 columns so the MMAs of tile i+1 overlap the epilogue of tile i), per-warp epilogue
+// staging slabs (32 rows x 32 columns) for coalesced stores.  TMEM allocation, barrier setup and
+// descriptor prefetch are paid once per CTA.
+constexpr int kMaxStagesP = 8;
+constexpr int kEpiWarps = 8;
 constexpr int kThreadsP = 64 + kEpiWarps * 32;     // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
-constexpr int kMaxBNP = 256;                       // the persistent kernel keeps 2 x BN-column accumulators (all 512 TMEM columns)
-constexpr int kSlabCols = kMaxBNP / 2;             // columns one epilogue warp handles per tile
-constexpr int kBookBytesP = 4096 + 8 * 2 * kSlabCols * 4;  // barriers etc. (first 4 KB) + per-warp scale/shift
+constexpr int kMaxBNP = 256;
+constexpr int kSlabChunk = 32;                     // columns staged per pass by an epilogue warp
+constexpr int kSlabPitch = kSlabChunk * 2 + 16;    // 80 B: odd multiple of 16 -> conflict-free 16-byte stores
+constexpr int kBookBytesP = 4096 + 4 * 2 * kMaxBNP * 4;           // barriers (first 4 KB) + [tile & 3][scale|shift][BN]
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-struct TileOrigin {
-  long long m0;
-  int n0, bn, bt0, bh0, bw0;
+struct HalfOrigin {
+  long long m0;            // first output pixel (linear) of this 128-row half (LINEAR / IM2COL)
+  int bn, bt0, bh0, bw0;   // BOX origin
 };
 
-__device__ __forceinline__ TileOrigin tile_origin(const ConvGeom& g, int tile) {
-  TileOrigin o;
-  const int m_tile = tile / g.n_tiles;
-  o.n0 = (tile - m_tile * g.n_tiles) * g.BN;
+__device__ __forceinline__ HalfOrigin half_origin(const ConvGeom& g, int m_tile) {
+  HalfOrigin o;
   o.m0 = (long long)m_tile * kBM;
   o.bn = o.bt0 = o.bh0 = o.bw0 = 0;
   if (g.mode == A_BOX) {
     int r = m_tile;
     o.bw0 = (r % g.tiles_w) * g.bw; r /= g.tiles_w;
     o.bh0 = (r % g.tiles_h) * g.bh; r /= g.tiles_h;
-    o.bt0 = (r % g.tiles_t) * g.bt; o.bn = r / g.tiles_t;
+    o.bt0 = (r % g.tiles_t) * g.bt; o.bn = r / g.tiles_t;   // bn >= Nimg: the whole box is out of bounds -> zeros
   }
   return o;
 }
@@ -380,32 +387,33 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   constexpr int kABytes = kBM * BK * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint64_t* full_bar = (uint64_t*)smem_raw;
-  uint64_t* empty_bar = full_bar + kStagesP;
-  uint64_t* tfull_bar = empty_bar + kStagesP;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint64_t* empty_bar = full_bar + kMaxStagesP;
+  uint64_t* tfull_bar = empty_bar + kMaxStagesP;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint32_t* tmem_ptr_s = (uint32_t*)(tempty_bar + 2);
-  float* ss_all = (float*)(smem_raw + 4096);    // [kEpiWarps][2][kSlabCols]
+  float* ss_all = (float*)(smem_raw + 4096);       // [tile & 3][scale | shift][kMaxBNP]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + kBookBytesP + 1023) & ~(uintptr_t)1023);
+  const int mh = g.mh;
   const int b_bytes = g.BN * BK * 2;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + g.n_stages_p * kABytes;
-  uint8_t* slabs = sB + g.n_stages_p * b_bytes;  // [kEpiWarps][32 rows][slab_pitch]
-  const int kSlabPitch = g.slab_pitch;
+  const int stage_bytes = mh * kABytes + b_bytes;  // multiple of 1024 (BN % 16 == 0)
+  uint8_t* slabs = smem + (size_t)g.n_stages_p * stage_bytes;   // [kEpiWarps][32 rows][kSlabPitch]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = g.taps * g.kblocks_per_tap;
+  const int nbuf = g.tmem_bufs;                    // 1 or 2 accumulator sets
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-    for (int s = 0; s < kStagesP; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < g.n_stages_p; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiWarps); }
     fence_barrier_init();
   }
   uint32_t ncols = 32;
   while (ncols < (uint32_t)g.BN) ncols <<= 1;
+  const uint32_t alloc_cols = ncols * (uint32_t)(mh * nbuf);   // <= 512 by construction (host)
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(2 * ncols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(alloc_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -416,34 +424,41 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      const uint32_t tx_bytes = (uint32_t)(g.a_bytes + b_bytes);
+      const uint32_t tx_bytes = (uint32_t)(mh * g.a_bytes + b_bytes);
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileOrigin o = tile_origin(g, tile);
-        int iw = 0, ih = 0, it = 0, in_ = 0;
-        if (g.mode == A_IM2COL) {
-          long long r = o.m0;
-          iw = (int)(r % g.OW); r /= g.OW;
-          ih = (int)(r % g.OH); r /= g.OH;
-          it = (int)(r % g.OT); in_ = (int)(r / g.OT);
-          iw -= g.PW; ih -= g.PH; it -= g.PT;
+        const int mt = tile / g.n_tiles;
+        const int n0 = (tile - mt * g.n_tiles) * g.BN;
+        HalfOrigin ho[2];
+        int iw[2], ih[2], it[2], in_[2];
+        for (int h = 0; h < mh; ++h) {
+          ho[h] = half_origin(g, mt * mh + h);
+          long long r = ho[h].m0;
+          iw[h] = (int)(r % g.OW); r /= g.OW;
+          ih[h] = (int)(r % g.OH); r /= g.OH;
+          it[h] = (int)(r % g.OT); in_[h] = (int)(r / g.OT);   // in_ >= Nimg: out of bounds -> zeros
+          iw[h] -= g.PW; ih[h] -= g.PH; it[h] -= g.PT;
         }
         for (int tap = 0; tap < g.taps; ++tap) {
           const int kw = tap % g.KW, kh = (tap / g.KW) % g.KH, kt = tap / (g.KW * g.KH);
           for (int kc = 0; kc < g.kblocks_per_tap; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], tx_bytes);
-            void* a_dst = sA + stage * kABytes;
-            void* b_dst = sB + stage * b_bytes;
+            uint8_t* st = smem + (size_t)stage * stage_bytes;
             const int c0 = kc * BK;
-            if (g.mode == A_LINEAR) {
-              tma_load_2d(&map_a, &full_bar[stage], a_dst, c0, (int)o.m0);
-            } else if (g.mode == A_BOX) {
-              tma_load_5d(&map_a, &full_bar[stage], a_dst, c0, o.bw0 + kw - g.PW, o.bh0 + kh - g.PH, o.bt0 + kt - g.PT, o.bn);
-            } else {
-              tma_load_im2col_5d(&map_a, &full_bar[stage], a_dst, c0, iw, ih, it, in_, (uint16_t)kw, (uint16_t)kh, (uint16_t)kt);
+            for (int h = 0; h < mh; ++h) {
+              void* a_dst = st + h * kABytes;
+              if (g.mode == A_LINEAR) {
+                tma_load_2d(&map_a, &full_bar[stage], a_dst, c0, (int)ho[h].m0);
+              } else if (g.mode == A_BOX) {
+                tma_load_5d(&map_a, &full_bar[stage], a_dst, c0, ho[h].bw0 + kw - g.PW, ho[h].bh0 + kh - g.PH,
+                            ho[h].bt0 + kt - g.PT, ho[h].bn);
+              } else {
+                tma_load_im2col_5d(&map_a, &full_bar[stage], a_dst, c0, iw[h], ih[h], it[h], in_[h], (uint16_t)kw,
+                                   (uint16_t)kh, (uint16_t)kt);
+              }
             }
-            tma_load_3d(&map_b, &full_bar[stage], b_dst, c0, tap, o.n0);
+            tma_load_3d(&map_b, &full_bar[stage], st + mh * kABytes, c0, tap, n0);
             if (++stage == g.n_stages_p) { stage = 0; phase ^= 1; }
           }
         }
@@ -454,20 +469,24 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     int stage = 0; uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(&tempty_bar[buf], tphase ^ 1);   // epilogue has drained this accumulator
+      const int buf = nbuf == 2 ? (it & 1) : 0;
+      const uint32_t use = (uint32_t)(nbuf == 2 ? (it >> 1) : it);
+      mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // the epilogue has drained this accumulator set
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)buf * ncols;
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * mh) * ncols;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_addr = smem_u32(sA + stage * kABytes), b_addr = smem_u32(sB + stage * b_bytes);
+          const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = st + mh * kABytes;
+          for (int h = 0; h < mh; ++h) {
+            const uint32_t a_addr = st + h * kABytes;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16(tmem_d, make_smem_desc<BK>(a_addr + k * 32), make_smem_desc<BK>(b_addr + k * 32), g.idesc,
-                     (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16(tmem_d + (uint32_t)h * ncols, make_smem_desc<BK>(a_addr + k * 32), make_smem_desc<BK>(b_addr + k * 32),
+                       g.idesc, (kb | k) ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) umma_commit(&tfull_bar[buf]);
         }
@@ -477,120 +496,131 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
+    // mh == 2: warp = (lane quarter, row half), all BN columns.  mh == 1: warp = (lane quarter, column half).
     const int ew = warp - 2;
     const int lane_grp = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                      // which column half of the tile
-    const int chunks = g.BN >> 4;                  // 16-column chunks in the tile
-    const int ch_begin = half ? (chunks + 1) / 2 : 0;
-    const int ch_end = half ? chunks : (chunks + 1) / 2;
-    const int col0 = ch_begin * 16, ncol = (ch_end - ch_begin) * 16;
-    float* s_scale = ss_all + (size_t)ew * 2 * kSlabCols;
-    float* s_shift = s_scale + kSlabCols;
+    const int sel = ew >> 2;                       // 0 / 1
+    const int hsel = mh == 2 ? sel : 0;            // which 128-row half
+    const int chunks16 = g.BN >> 4;
+    const int col0 = (mh == 2 || sel == 0) ? 0 : ((chunks16 + 1) / 2) * 16;
+    const int col1 = (mh == 2 || sel == 1) ? g.BN : ((chunks16 + 1) / 2) * 16;
+    const int ncol = col1 - col0;                  // multiple of 16, may be 0
     uint8_t* slab = slabs + (size_t)ew * 32 * kSlabPitch;
     uint8_t* srow = slab + (size_t)lane * kSlabPitch;
     const int row = lane_grp * 32 + lane;
-    // row -> output pixel of a tile
-    auto row_pixel = [&](const TileOrigin& o) -> long long {
+    auto row_pixel = [&](int m_tile) -> long long {
+      const HalfOrigin o = half_origin(g, m_tile);
       if (g.mode == A_BOX) {
         int dw = row % g.bw, r = row / g.bw;
         int dh = r % g.bh, dt = r / g.bh;
         int ow = o.bw0 + dw, oh = o.bh0 + dh, ot = o.bt0 + dt;
-        if (dt < g.bt && ow < g.OW && oh < g.OH && ot < g.OT) return (((long long)o.bn * g.OT + ot) * g.OH + oh) * g.OW + ow;
+        if (o.bn < g.Nimg && dt < g.bt && ow < g.OW && oh < g.OH && ot < g.OT)
+          return (((long long)o.bn * g.OT + ot) * g.OH + oh) * g.OW + ow;
         return -1;
       }
       long long m = o.m0 + row;
       return m < g.M ? m : -1;
     };
-    // Residual rows (two_branch.py:79-81) are row-strided 16-byte loads: they are issued for tile i+1 right
-    // after tile i's accumulator has been drained, so their latency hides behind the copy-out of tile i
-    // and the MMAs of tile i+1 instead of stalling the epilogue.
-    uint4 rreg[kSlabCols / 8];
-    auto prefetch_residual = [&](int tile) {
-      if (!kHasRes || tile >= total_tiles) return;
-      const TileOrigin o = tile_origin(g, tile);
-      const long long px = row_pixel(o);
-      const int nb = o.n0 + col0;
-      const __half* rrow = residual + (px < 0 ? 0 : (size_t)px * g.res_ld + g.res_coff + nb);
-#pragma unroll
-      for (int j = 0; j < kSlabCols / 8; ++j) {
-        rreg[j] = make_uint4(0, 0, 0, 0);
-        if (px >= 0 && j * 8 < ncol && nb + j * 8 < g.Cout) rreg[j] = *reinterpret_cast<const uint4*>(rrow + j * 8);
-      }
-    };
-    prefetch_residual(blockIdx.x);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      const TileOrigin o = tile_origin(g, tile);
-      const long long pix = row_pixel(o);
-      const int nbase = o.n0 + col0;               // first output channel this warp handles
+      const int buf = nbuf == 2 ? (it & 1) : 0;
+      const uint32_t use = (uint32_t)(nbuf == 2 ? (it >> 1) : it);
+      const int mt = tile / g.n_tiles;
+      const int n0 = (tile - mt * g.n_tiles) * g.BN;
+      const long long pix = row_pixel(mt * mh + hsel);
+      const int nbase = n0 + col0;                 // first output channel this warp handles
+      // per-channel epilogue constants of this tile; warps of the same tile write identical values into
+      // slot (tile & 3): a warp reaches this point at most two tiles ahead of the slowest warp (it cannot
+      // pass the tfull wait of tile i+2 before every warp released the accumulator of tile i)
+      float* s_scale = ss_all + (size_t)(it & 3) * 2 * kMaxBNP + col0;
+      float* s_shift = s_scale + kMaxBNP;
       for (int i = lane; i < ncol; i += 32) {
         const int c = nbase + i;
         s_scale[i] = (scale && c < g.Cout) ? scale[c] : 1.0f;
         s_shift[i] = (shift && c < g.Cout) ? shift[c] : 0.0f;
       }
       __syncwarp();
-      mbar_wait(&tfull_bar[buf], tphase);
+      mbar_wait(&tfull_bar[buf], use & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)buf * ncols + (uint32_t)col0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * mh + hsel) * ncols + (uint32_t)col0;
+      const __half* rrow = (kHasRes && pix >= 0) ? residual + (size_t)pix * g.res_ld + g.res_coff + nbase : nullptr;
+      for (int cb = 0; cb < ncol; cb += kSlabChunk) {
+        const int cw = min(kSlabChunk, ncol - cb);   // 16 or 32 columns in this pass
+        // residual for this pass: row-strided 16-byte loads, issued before the TMEM read so they overlap it
+        uint4 rreg[kSlabChunk / 8];
+        if (kHasRes) {
 #pragma unroll
-      for (int ci = 0; ci < kSlabCols / 16; ++ci) {
-        const int c = ci * 16;
-        if (c >= ncol) break;
-        uint32_t v[16];
-        tmem_ld16(taddr + c, v);
-        tmem_ld_wait();
+          for (int j = 0; j < kSlabChunk / 8; ++j) {
+            rreg[j] = make_uint4(0, 0, 0, 0);
+            if (rrow && j * 8 < cw && nbase + cb + j * 8 < g.Cout) rreg[j] = *reinterpret_cast<const uint4*>(rrow + cb + j * 8);
+          }
+        }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int cc = c + h * 8;
-          float f[8];
+        for (int ci = 0; ci < kSlabChunk / 16; ++ci) {
+          const int c = cb + ci * 16;
+          if (ci * 16 >= cw) break;
+          uint32_t v[16];
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[h * 8 + k]), s_scale[cc + k], s_shift[cc + k]);
-          if (kHasRes) {
-            const __half2* hp = reinterpret_cast<const __half2*>(&rreg[ci * 2 + h]);
+          for (int h = 0; h < 2; ++h) {
+            const int cc = c + h * 8;
+            float f[8];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float2 rf = __half22float2(hp[k]);
-              f[2 * k] += rf.x; f[2 * k + 1] += rf.y;
+            for (int k = 0; k < 8; ++k) f[k] = fmaf(__uint_as_float(v[h * 8 + k]), s_scale[cc + k], s_shift[cc + k]);
+            if (kHasRes) {
+              const __half2* hp = reinterpret_cast<const __half2*>(&rreg[ci * 2 + h]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float2 rf = __half22float2(hp[k]);
+                f[2 * k] += rf.x; f[2 * k + 1] += rf.y;
+              }
             }
-          }
-          if (g.relu) {
+            if (g.relu) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+              for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+            }
+            store16(reinterpret_cast<__half*>(srow + (ci * 16 + h * 8) * 2), f);
           }
-          store16(reinterpret_cast<__half*>(srow + cc * 2), f);
         }
-      }
-      // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-      prefetch_residual(tile + gridDim.x);
-      // coalesced copy-out of this warp's 32 x ncol slab
-      const int cpr = ncol >> 3;
-      for (int i = lane; i < 32 * cpr; i += 32) {
-        const int rr = i / cpr, ch = i - rr * cpr;
-        const long long rp = __shfl_sync(0xffffffffu, pix, rr);
-        const int col = nbase + ch * 8;
-        if (rp >= 0 && col < g.Cout) {
-          uint4 val = *reinterpret_cast<const uint4*>(slab + (size_t)rr * kSlabPitch + ch * 16);
-          __half* dst = y + (size_t)rp * g.out_ld + g.out_coff + col;
-          if (g.n_splits > 0 && col >= g.split[0]) {
-            const int d = (g.n_splits > 1 && col >= g.split[1]) ? 1 : 0;
-            dst = g.y_extra[d] + (size_t)rp * g.ld_extra[d] + g.coff_extra[d] + (col - g.split[d]);
+        if (cb + kSlabChunk >= ncol) {
+          // last pass: the accumulator is fully read by this warp -> hand the TMEM set back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        } else {
+          __syncwarp();
+        }
+        // coalesced copy-out of the 32 x cw slab: consecutive lanes write consecutive 16-byte chunks of a row
+        const int cpr = cw >> 3;
+        for (int i = lane; i < 32 * cpr; i += 32) {
+          const int rr = i / cpr, ch = i - rr * cpr;
+          const long long rp = __shfl_sync(0xffffffffu, pix, rr);
+          const int col = nbase + cb + ch * 8;
+          if (rp >= 0 && col < g.Cout) {
+            uint4 val = *reinterpret_cast<const uint4*>(slab + (size_t)rr * kSlabPitch + ch * 16);
+            __half* dst = y + (size_t)rp * g.out_ld + g.out_coff + col;
+            if (g.n_splits > 0 && col >= g.split[0]) {
+              const int d = (g.n_splits > 1 && col >= g.split[1]) ? 1 : 0;
+              dst = g.y_extra[d] + (size_t)rp * g.ld_extra[d] + g.coff_extra[d] + (col - g.split[d]);
+            }
+            *reinterpret_cast<uint4*>(dst) = val;
           }
-          *reinterpret_cast<uint4*>(dst) = val;
         }
+        __syncwarp();
       }
-      __syncwarp();
+      if (ncol == 0) {  // this warp owns no columns (tiny BN): still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ncols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(alloc_cols) : "memory");
   }
 }
 
@@ -664,7 +694,7 @@ static int pick_bk(int Cin) {
   const int cands[3] = {64, 32, 16};
   for (int i = 0; i < 3; ++i) {
     int bk = cands[i];
-    long cost = (long)((Cin + bk - 1) / bk) * (bk + 8);  // padded K plus a per-k-block overhead term
+    long cost = (long)((Cin + bk - 1) / bk) * (bk + 16);  // padded K plus a per-k-block overhead term (measured: 160 -> 3x64 beats 5x32)
     if (best_cost < 0 || cost < best_cost) { best = bk; best_cost = cost; }
   }
   return best;
@@ -698,6 +728,8 @@ struct ConvPlan {
   int BK;
   size_t smem_bytes;
   dim3 grid;
+  int persist_tiles;
+  size_t persist_smem;
 };
 
 static int build_plan(const step_conv_params* p, ConvPlan* pl) {
@@ -722,23 +754,21 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   pl->BK = pick_bk(p->Cin);
   const int BK = pl->BK;
   g.kblocks_per_tap = (p->Cin + BK - 1) / BK;
+  long long m128 = 0;   // number of 128-row M tiles (filled in below once the A mode is known)
+  const bool persist = conv_variant() == 2;
   {
-    // N tile: as wide as the accumulator allows -- every N tile re-reads the whole A operand through L2,
-    // which is what bounds the k>1 layers.  Residual layers and the persistent (1x1) variant stay <= 128.
-    const bool persist = taps == 1 && conv_variant() == 2;
+    // N tile: as wide as the accumulator allows -- every N tile re-reads the whole A operand through L2.
     const int cap = persist ? kMaxBNP : (p->residual ? kMaxBNRes : kMaxBN);
     g.n_tiles = (p->Cout + cap - 1) / cap;
     g.BN = (((p->Cout + g.n_tiles - 1) / g.n_tiles) + 15) / 16 * 16;
     g.n_stages = g.BN > 128 ? 2 : 3;
-    g.n_stages_p = g.BN > 128 ? 3 : 5;
-    g.slab_pitch = (((g.BN >> 4) + 1) / 2) * 16 * 2 + 16;
   }
   g.Cout = p->Cout; g.out_ld = p->out_ld; g.out_coff = p->out_coff; g.res_ld = p->res_ld; g.res_coff = p->res_coff;
   g.relu = p->relu;
   g.n_splits = p->n_splits;
   if (p->n_splits) {
-    STEP_CHECK_ARG(p->n_splits >= 1 && p->n_splits <= 2 && taps == 1 && conv_variant() == 2 && !p->residual,
-                   "conv3d(f16): fused outputs need a 1x1x1 filter (persistent kernel), no residual, 1-2 splits");
+    STEP_CHECK_ARG(p->n_splits >= 1 && p->n_splits <= 2 && conv_variant() == 2 && !p->residual,
+                   "conv3d(f16): fused outputs need the persistent kernel, no residual, 1-2 splits");
     int prev = 0;
     for (int i = 0; i < p->n_splits; ++i) {
       STEP_CHECK_ARG(p->split[i] % 16 == 0 && p->split[i] > prev && p->split[i] < p->Cout && p->y_extra[i] &&
@@ -818,6 +848,21 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
     size_t out_tile = (size_t)kBM * (g.BN * 2 + 16);
     pl->smem_bytes = kBookBytes + 1024 + (stage_area > out_tile ? stage_area : out_tile);
   }
+  // persistent kernel: two 128-row halves per tile when that still leaves at least one full wave of tiles
+  m128 = m_tiles;
+  g.mh = ((m128 + 1) / 2) * g.n_tiles >= kNumSMs ? 2 : 1;
+  {
+    int ncols = 32;
+    while (ncols < g.BN) ncols <<= 1;
+    g.tmem_bufs = (g.mh * ncols * 2 <= 512) ? 2 : 1;
+    const size_t budget = 227 * 1024 - kBookBytesP - 1024 - (size_t)kEpiWarps * 32 * kSlabPitch;
+    const size_t stage_bytes = (size_t)g.mh * kBM * BK * 2 + (size_t)g.BN * BK * 2;
+    int st = (int)(budget / stage_bytes);
+    g.n_stages_p = st > kMaxStagesP ? kMaxStagesP : st;
+    STEP_CHECK_ARG(g.n_stages_p >= 2, "conv3d(f16): tile does not fit shared memory");
+    pl->persist_tiles = (int)(((m128 + g.mh - 1) / g.mh) * g.n_tiles);
+    pl->persist_smem = kBookBytesP + 1024 + (size_t)g.n_stages_p * stage_bytes + (size_t)kEpiWarps * 32 * kSlabPitch;
+  }
   return 0;
 }
 
@@ -837,18 +882,17 @@ static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t
 
 template <int BK, bool kHasRes>
 static int launch_persist(const ConvPlan& pl, const step_conv_params* p, cudaStream_t s) {
-  const size_t smem = kBookBytesP + 1024 + (size_t)pl.g.n_stages_p * (kBM * BK * 2 + pl.g.BN * BK * 2) +
-                      (size_t)kEpiWarps * 32 * pl.g.slab_pitch;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_persist_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv3d(f16): smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int total = (int)pl.grid.x;
+  const int total = pl.persist_tiles;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  conv_umma_persist_kernel<BK, kHasRes><<<grid, kThreadsP, smem, s>>>(pl.map_a, pl.map_b, pl.g, total, p->scale, p->shift,
-                                                                     (const __half*)p->residual, (__half*)p->y);
+  conv_umma_persist_kernel<BK, kHasRes><<<grid, kThreadsP, pl.persist_smem, s>>>(pl.map_a, pl.map_b, pl.g, total, p->scale,
+                                                                                p->shift, (const __half*)p->residual,
+                                                                                (__half*)p->y);
   STEP_LAUNCH_CHECK("conv_umma_persist_kernel");
   return 0;
 }
@@ -857,9 +901,8 @@ int conv3d_umma_launch(const step_conv_params* p, step_stream_t stream) {
   ConvPlan pl;
   if (int rc = build_plan(p, &pl)) return rc;
   const bool res = p->residual != nullptr;
-  // persistent kernel for 1x1x1 filters (short K loops: per-CTA setup and the epilogue dominate);
-  // one-tile-per-CTA x 2 CTAs/SM for k>1 (long K loops: two producer/MMA threads per SM keep more TMA in flight)
-  if (conv_variant() == 2 && pl.g.taps == 1) {
+  // default: the persistent kernel; STEP_B200_CONV=1 selects the one-tile-per-CTA kernel (2 CTAs/SM) for A/B runs
+  if (conv_variant() == 2) {
     if (pl.BK == 64) return res ? launch_persist<64, true>(pl, p, cu(stream)) : launch_persist<64, false>(pl, p, cu(stream));
     if (pl.BK == 32) return res ? launch_persist<32, true>(pl, p, cu(stream)) : launch_persist<32, false>(pl, p, cu(stream));
     return res ? launch_persist<16, true>(pl, p, cu(stream)) : launch_persist<16, false>(pl, p, cu(stream));
