@@ -354,6 +354,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreadsP = 64 + kEpiWarps * 32;     // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
 constexpr int kMaxBNP = 256;
 constexpr int kSlabChunk = 32;                     // columns staged per pass by an epilogue warp
+constexpr int kResPrefetch = 16;                   // 16-byte residual chunks (= 128 columns) prefetched per row
 constexpr int kSlabPitch = kSlabChunk * 2 + 16;    // 80 B: odd multiple of 16 -> conflict-free 16-byte stores
 constexpr int kBookBytesP = 4096 + 4 * 2 * kMaxBNP * 4;           // barriers (first 4 KB) + [tile & 3][scale|shift][BN]
 
@@ -539,6 +540,17 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         s_scale[i] = (scale && c < g.Cout) ? scale[c] : 1.0f;
         s_shift[i] = (shift && c < g.Cout) ? shift[c] : 0.0f;
       }
+      // Residual (two_branch.py:79-81): the row-strided 16-byte loads of this warp's first 128 columns are issued
+      // before waiting for the accumulator so their latency overlaps the MMAs of this tile.
+      uint4 rpre[kResPrefetch];
+      if (kHasRes) {
+        const __half* rr0 = pix >= 0 ? residual + (size_t)pix * g.res_ld + g.res_coff + nbase : nullptr;
+#pragma unroll
+        for (int j = 0; j < kResPrefetch; ++j) {
+          rpre[j] = make_uint4(0, 0, 0, 0);
+          if (rr0 && j * 8 < ncol && nbase + j * 8 < g.Cout) rpre[j] = *reinterpret_cast<const uint4*>(rr0 + j * 8);
+        }
+      }
       __syncwarp();
       mbar_wait(&tfull_bar[buf], use & 1u);
       tc_fence_after();
@@ -546,13 +558,16 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       const __half* rrow = (kHasRes && pix >= 0) ? residual + (size_t)pix * g.res_ld + g.res_coff + nbase : nullptr;
       for (int cb = 0; cb < ncol; cb += kSlabChunk) {
         const int cw = min(kSlabChunk, ncol - cb);   // 16 or 32 columns in this pass
-        // residual for this pass: row-strided 16-byte loads, issued before the TMEM read so they overlap it
         uint4 rreg[kSlabChunk / 8];
         if (kHasRes) {
 #pragma unroll
           for (int j = 0; j < kSlabChunk / 8; ++j) {
-            rreg[j] = make_uint4(0, 0, 0, 0);
-            if (rrow && j * 8 < cw && nbase + cb + j * 8 < g.Cout) rreg[j] = *reinterpret_cast<const uint4*>(rrow + cb + j * 8);
+            const int pj = cb / 8 + j;               // 16-byte chunk index within this warp's columns
+            if (pj < kResPrefetch) rreg[j] = rpre[pj];
+            else {
+              rreg[j] = make_uint4(0, 0, 0, 0);
+              if (rrow && j * 8 < cw && nbase + cb + j * 8 < g.Cout) rreg[j] = *reinterpret_cast<const uint4*>(rrow + cb + j * 8);
+            }
           }
         }
 #pragma unroll
@@ -717,7 +732,7 @@ static int conv_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("STEP_B200_CONV");
-    v = (e && e[0] == '1') ? 1 : 2;   // 1 = one tile per CTA (2 CTAs/SM), 2 = persistent (default)
+    v = (e && e[0] == '1') ? 1 : ((e && e[0] == '3') ? 3 : 2);   // 2 (default) = hybrid, see conv3d_umma_launch
   }
   return v;
 }
@@ -755,7 +770,7 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   const int BK = pl->BK;
   g.kblocks_per_tap = (p->Cin + BK - 1) / BK;
   long long m128 = 0;   // number of 128-row M tiles (filled in below once the A mode is known)
-  const bool persist = conv_variant() == 2;
+  const bool persist = conv_variant() == 3 || (conv_variant() == 2 && taps == 1);
   {
     // N tile: as wide as the accumulator allows -- every N tile re-reads the whole A operand through L2.
     const int cap = persist ? kMaxBNP : (p->residual ? kMaxBNRes : kMaxBN);
@@ -767,7 +782,7 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   g.relu = p->relu;
   g.n_splits = p->n_splits;
   if (p->n_splits) {
-    STEP_CHECK_ARG(p->n_splits >= 1 && p->n_splits <= 2 && conv_variant() == 2 && !p->residual,
+    STEP_CHECK_ARG(p->n_splits >= 1 && p->n_splits <= 2 && persist && !p->residual,
                    "conv3d(f16): fused outputs need the persistent kernel, no residual, 1-2 splits");
     int prev = 0;
     for (int i = 0; i < p->n_splits; ++i) {
@@ -850,7 +865,8 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   }
   // persistent kernel: two 128-row halves per tile when that still leaves at least one full wave of tiles
   m128 = m_tiles;
-  g.mh = ((m128 + 1) / 2) * g.n_tiles >= kNumSMs ? 2 : 1;
+  g.mh = (conv_variant() == 3 && ((m128 + 1) / 2) * g.n_tiles >= kNumSMs) ? 2 : 1;
+  if (const char* e = getenv("STEP_B200_MH")) { if (e[0] == '1') g.mh = 1; else if (e[0] == '2') g.mh = 2; }
   {
     int ncols = 32;
     while (ncols < g.BN) ncols <<= 1;
@@ -859,6 +875,7 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
     const size_t stage_bytes = (size_t)g.mh * kBM * BK * 2 + (size_t)g.BN * BK * 2;
     int st = (int)(budget / stage_bytes);
     g.n_stages_p = st > kMaxStagesP ? kMaxStagesP : st;
+    if (const char* e = getenv("STEP_B200_STAGES")) { int v = atoi(e); if (v >= 2 && v < g.n_stages_p) g.n_stages_p = v; }
     STEP_CHECK_ARG(g.n_stages_p >= 2, "conv3d(f16): tile does not fit shared memory");
     pl->persist_tiles = (int)(((m128 + g.mh - 1) / g.mh) * g.n_tiles);
     pl->persist_smem = kBookBytesP + 1024 + (size_t)g.n_stages_p * stage_bytes + (size_t)kEpiWarps * 32 * kSlabPitch;
@@ -901,8 +918,11 @@ int conv3d_umma_launch(const step_conv_params* p, step_stream_t stream) {
   ConvPlan pl;
   if (int rc = build_plan(p, &pl)) return rc;
   const bool res = p->residual != nullptr;
-  // default: the persistent kernel; STEP_B200_CONV=1 selects the one-tile-per-CTA kernel (2 CTAs/SM) for A/B runs
-  if (conv_variant() == 2) {
+  // Measured per layer (tools/conv_bench.py, profiles/): the persistent kernel wins on 1x1x1 filters (short K
+  // loops: per-CTA setup + epilogue dominate, wide N tiles); for k > 1 the one-tile-per-CTA kernel with 2-5
+  // co-resident CTAs per SM keeps more TMA requests in flight and wins, by 2x on the BK=32 stem.
+  // STEP_B200_CONV=1 forces one-tile-per-CTA everywhere, =3 forces the persistent kernel everywhere.
+  if (conv_variant() == 3 || (conv_variant() == 2 && pl.g.taps == 1)) {
     if (pl.BK == 64) return res ? launch_persist<64, true>(pl, p, cu(stream)) : launch_persist<64, false>(pl, p, cu(stream));
     if (pl.BK == 32) return res ? launch_persist<32, true>(pl, p, cu(stream)) : launch_persist<32, false>(pl, p, cu(stream));
     return res ? launch_persist<16, true>(pl, p, cu(stream)) : launch_persist<16, false>(pl, p, cu(stream));

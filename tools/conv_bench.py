@@ -1,0 +1,44 @@
+"""Time individual conv layers of the C4 workload through the C ABI (CUDA events, 20 reps after 3 warm-ups).
+Knobs via env: STEP_B200_CONV (1 = one tile per CTA, 2 = persistent), STEP_B200_MH, STEP_B200_STAGES, STEP_B200_AMODE."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from step_b200 import _lib as L, engine as E
+from step_b200.engine import Act
+
+LAYERS = {
+    # name: (N, T, H, W, Cin, Cout, k, pad, residual)
+    "stem_s2d":   (8, 16, 112, 112, 32, 64, (4, 4, 4), (1, 1, 1), False),
+    "conv2c":     (8, 16, 56, 56, 64, 192, (3, 3, 3), None, False),
+    "3b_b1b":     (8, 16, 28, 28, 96, 128, (3, 3, 3), None, False),
+    "3c_b1b":     (8, 16, 28, 28, 128, 192, (3, 3, 3), None, False),
+    "4f_b1b":     (8, 8, 14, 14, 160, 320, (3, 3, 3), None, False),
+    "5b_b1b":     (88, 8, 7, 7, 160, 320, (3, 3, 3), None, False),
+    "5c_b1b":     (88, 8, 7, 7, 192, 384, (3, 3, 3), None, False),
+    "loc_1088":   (704, 1, 7, 7, 1088, 1024, (1, 1, 1), None, False),
+    "loc_3x3":    (704, 1, 7, 7, 256, 256, (1, 3, 3), None, False),
+    "loc_res":    (704, 1, 7, 7, 256, 1024, (1, 1, 1), None, True),
+    "loc_1024":   (704, 1, 7, 7, 1024, 256, (1, 1, 1), None, False),
+    "5b_fused":   (88, 8, 7, 7, 832, 448, (1, 1, 1), None, False),
+    "4b_fused":   (8, 8, 14, 14, 480, 304, (1, 1, 1), None, False),
+}
+names = sys.argv[1:] or list(LAYERS)
+torch.manual_seed(0)
+for name in names:
+    N, T, H, W, Cin, Cout, k, pad, res = LAYERS[name]
+    x = Act(torch.randn(N, T, H, W, Cin, device="cuda").half())
+    w = (torch.randn(Cout, k[0] * k[1] * k[2], Cin, device="cuda") / (Cin * k[0] * k[1] * k[2]) ** 0.5).half()
+    out = Act(torch.empty(N, T, H, W, Cout, device="cuda", dtype=torch.float16))
+    r = Act(torch.randn(N, T, H, W, Cout, device="cuda").half()) if res else None
+    sc = torch.ones(Cout, device="cuda"); sh = torch.zeros(Cout, device="cuda")
+    f = lambda: E.conv(x, w, sc, sh, out, k, (1, 1, 1), pad, True, r)
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps): f()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    gf = 2.0 * N * T * H * W * Cin * Cout * k[0] * k[1] * k[2] / 1e9
+    print("%-10s %8.1f us  %7.1f TFLOP/s (padded-K flops %.1f G)" % (name, us, gf / us / 1e3, gf))
