@@ -41,4 +41,4 @@ for name in names:
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
     gf = 2.0 * N * T * H * W * Cin * Cout * k[0] * k[1] * k[2] / 1e9
-    print("%-10s %8.1f us  %7.1f TFLOP/s (padded-K flops %.1f G)" % (name, us, gf / us / 1e3, gf))
+    print("%-10s %8.1f us  %7.1f TFLOP/s  %4.1f%% of 1451 (algorithmic %.1f GFLOP)" % (name, us, gf / us * 1e3, gf / us * 1e3 / 14.511, gf))
