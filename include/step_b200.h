@@ -81,10 +81,13 @@ int step_roi_pool_bwd_nchw_f32(const float* grad_out, const int32_t* argmax, con
  * C must be a multiple of 8 (f16) / 4 (f32); feat_ld, out_ld likewise.
  * Frame map: ROI column 0 indexes frames of the slice conv_feat[:, t_start:t_start+roi_T]
  * (utils/utils.py:48); with roi_T > 0 the kernel reads frame (f / roi_T) * feat_T + t_start + f % roi_T
- * of the full map instead of needing the slice copied.  roi_T == 0: identity. */
+ * of the full map instead of needing the slice copied.  roi_T == 0: identity.
+ * exact != 0: reference operation order, bit-identical (always used for f32).  exact == 0 with f16 storage:
+ * 1/count folded into the tap weights, one fp32 FMA per tap -- within one fp16 ulp of the exact result. */
 int step_roi_align_fwd_nhwc(const void* feat, int dtype, int K, int H, int W, int C, int feat_ld,
                             const float* rois, int R, float scale, int ph, int pw, int sampling_ratio,
-                            void* out, int out_ld, int roi_T, int feat_T, int t_start, step_stream_t stream);
+                            void* out, int out_ld, int roi_T, int feat_T, int t_start, int exact,
+                            step_stream_t stream);
 int step_roi_pool_fwd_nhwc(const void* feat, int dtype, int K, int H, int W, int C, int feat_ld,
                            const float* rois, int R, float scale, int ph, int pw, void* out, int out_ld,
                            int roi_T, int feat_T, int t_start, step_stream_t stream);
@@ -179,6 +182,14 @@ size_t step_linear_small_n_workspace_bytes(int M, int K, int N);
 int step_linear_small_n(const void* x, int dtype, int M, int K, int x_ld, const void* w, const float* bias,
                         int N, float* y, int y_ld, int act, int accumulate, const int32_t* row_map,
                         void* workspace, size_t ws_bytes, step_stream_t stream);
+
+/* local_reg + neighbor_reg1 + neighbor_reg2 of TwoBranchNet (two_branch.py:261-270) in one pass over the
+ * [R*T, K] feature rows: w12 = [W_local | W_nb1 | W_nb2] (12 x K), bias12 likewise.  Writes
+ * local_loc [R,T,4], first_loc [R,s1-s0,4] = (local + nb1)[:, s0:s1], last_loc [R,e1-e0,4] = (local + nb2)[:, e0:e1].
+ * workspace: step_linear_small_n_workspace_bytes(R*T, K, 12). */
+int step_head_regress(const void* x, int dtype, int R, int T, int K, int x_ld, const void* w12, const float* bias12,
+                      int s0, int s1, int e0, int e1, float* local_loc, float* first, float* last, void* workspace,
+                      size_t ws_bytes, step_stream_t stream);
 
 #ifdef __cplusplus
 }

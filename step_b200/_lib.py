@@ -45,7 +45,7 @@ def _declare(lib):
         "step_roi_align_bwd_nchw_f32": ([P, P, I, Fl, I, I, I, I, I, I, I, P, S], c_int),
         "step_roi_pool_fwd_nchw_f32": ([P, I, I, I, I, P, I, Fl, I, I, P, P, S], c_int),
         "step_roi_pool_bwd_nchw_f32": ([P, P, P, I, I, I, I, I, I, I, P, S], c_int),
-        "step_roi_align_fwd_nhwc": ([P, I, I, I, I, I, I, P, I, Fl, I, I, I, P, I, I, I, I, S], c_int),
+        "step_roi_align_fwd_nhwc": ([P, I, I, I, I, I, I, P, I, Fl, I, I, I, P, I, I, I, I, I, S], c_int),
         "step_roi_pool_fwd_nhwc": ([P, I, I, I, I, I, I, P, I, Fl, I, I, P, I, I, I, I, S], c_int),
         "step_tube_decode_f32": ([P, I, P, I, P, S], c_int),
         "step_tube_encode_f32": ([P, P, I, I, P, S], c_int),
@@ -62,6 +62,7 @@ def _declare(lib):
         "step_mean_mid": ([P, I, I, I, I, I, I, P, I, S], c_int),
         "step_linear_small_n_workspace_bytes": ([I, I, I], c_size_t),
         "step_linear_small_n": ([P, I, I, I, I, P, P, I, P, I, I, I, P, P, c_size_t, S], c_int),
+        "step_head_regress": ([P, I, I, I, I, I, P, P, I, I, I, I, P, P, P, P, c_size_t, S], c_int),
         "step_debug_tma_tile": ([ctypes.POINTER(ConvParams), I, I, I, I, I, P, P, P, S], c_int),
     }
     for name, (argtypes, restype) in sigs.items():

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ x,
 // vectors: 512 contiguous bytes per warp per load), reduces them horizontally and folds the row into the
 // 7 accumulators: ~130 instead of ~460 instructions per output vector.
 template <typename T>
-__global__ void __launch_bounds__(256) maxpool3d_333_kernel(const T* __restrict__ x, int N, int T_, int H, int W, int C,
+__global__ void __launch_bounds__(256, 3) maxpool3d_333_kernel(const T* __restrict__ x, int N, int T_, int H, int W, int C,
                                                             int in_ld, T* __restrict__ y, int out_ld) {
   constexpr int VN = Vec16<T>::N, WB = 7;
   const int nvec = C / VN, wsegs = W / WB;
@@ -312,6 +312,29 @@ __global__ void linear_reduce_kernel(const float* __restrict__ partial, int kspl
   *dst = v;
 }
 
+// local_reg | neighbor_reg1 | neighbor_reg2 (two_branch.py:261-270) share their input: one split-K pass with the
+// twelve weight rows, then this reduction writes local_loc [R,T,4], first_loc = (local + nb1)[:, s0:s1] and
+// last_loc = (local + nb2)[:, e0:e1] in one go.  bias12 = [b_local | b_nb1 | b_nb2].
+__global__ void head_reg_reduce_kernel(const float* __restrict__ partial, int ksplit, int R, int T,
+                                       const float* __restrict__ bias12, int s0, int s1, int e0, int e1,
+                                       float* __restrict__ local_loc, float* __restrict__ first, float* __restrict__ last) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (row m = r*T + t, coordinate c)
+  const int M = R * T;
+  if (i >= M * 4) return;
+  const int m = i >> 2, c = i & 3;
+  float v[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float a = 0.0f;
+    for (int s = 0; s < ksplit; ++s) a += partial[((size_t)s * M + m) * 12 + j * 4 + c];
+    v[j] = a + bias12[j * 4 + c];
+  }
+  local_loc[i] = v[0];
+  const int r = m / T, t = m - r * T;
+  if (t >= s0 && t < s1) first[((size_t)r * (s1 - s0) + (t - s0)) * 4 + c] = v[0] + v[1];
+  if (t >= e0 && t < e1) last[((size_t)r * (e1 - e0) + (t - e0)) * 4 + c] = v[0] + v[2];
+}
+
 static int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   long long cap = (long long)kNumSMs * 16;
@@ -462,5 +485,33 @@ extern "C" int step_linear_small_n(const void* x, int dtype, int M, int K, int x
   linear_reduce_kernel<<<ceil_div((long long)M * N, 256), 256, 0, cu(stream)>>>((const float*)workspace, ksplit, M, N, bias,
                                                                                y, y_ld, act, accumulate);
   STEP_LAUNCH_CHECK("linear_reduce_kernel");
+  return 0;
+}
+
+extern "C" int step_head_regress(const void* x, int dtype, int R, int T, int K, int x_ld, const void* w12,
+                                 const float* bias12, int s0, int s1, int e0, int e1, float* local_loc, float* first,
+                                 float* last, void* workspace, size_t ws_bytes, step_stream_t stream) {
+  const int vn = dtype == STEP_F16 ? 8 : 4;
+  const int M = R * T;
+  STEP_CHECK_ARG(dtype == STEP_F16 || dtype == STEP_F32, "head_regress: bad dtype");
+  STEP_CHECK_ARG(x && w12 && bias12 && local_loc && first && last && R >= 0 && T > 0 && K > 0, "head_regress: bad args");
+  STEP_CHECK_ARG(0 <= s0 && s0 < s1 && s1 <= T && 0 <= e0 && e0 < e1 && e1 <= T, "head_regress: bad chunk ranges");
+  STEP_CHECK_ARG(K % vn == 0 && x_ld % vn == 0 && (((uintptr_t)x | (uintptr_t)w12) & 15) == 0, "head_regress: alignment");
+  if (M == 0) return 0;
+  const int ksplit = ceil_div(K, kLinKC);
+  if (!workspace || ws_bytes < step_linear_small_n_workspace_bytes(M, K, 12))
+    return fail(STEP_E_WORKSPACE, "head_regress: workspace %zu < %zu", ws_bytes, step_linear_small_n_workspace_bytes(M, K, 12));
+  dim3 grid(ksplit, ceil_div(M, kLinRows));
+  STEP_CHECK_ARG(grid.y <= 65535, "head_regress: too many rows");
+  if (dtype == STEP_F16)
+    linear_splitk_kernel<__half><<<grid, 256, 0, cu(stream)>>>((const __half*)x, M, K, x_ld, (const __half*)w12, 12, nullptr,
+                                                               (float*)workspace);
+  else
+    linear_splitk_kernel<float><<<grid, 256, 0, cu(stream)>>>((const float*)x, M, K, x_ld, (const float*)w12, 12, nullptr,
+                                                              (float*)workspace);
+  STEP_LAUNCH_CHECK("linear_splitk_kernel");
+  head_reg_reduce_kernel<<<ceil_div((long long)M * 4, 256), 256, 0, cu(stream)>>>((const float*)workspace, ksplit, R, T, bias12,
+                                                                                 s0, s1, e0, e1, local_loc, first, last);
+  STEP_LAUNCH_CHECK("head_reg_reduce_kernel");
   return 0;
 }

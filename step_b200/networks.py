@@ -94,7 +94,10 @@ class ROINet(nn.Module):
                 L.ptr(flat_tubes), R, 1.0 / 16.0, ps, ps]
         if self.pool_mode == 'align':
             args.append(0)
-        args += [L.c_void_p(out.data_ptr()), out.ld, roi_T, feat_T, t_start, L.stream()]
+        args += [L.c_void_p(out.data_ptr()), out.ld, roi_T, feat_T, t_start]
+        if self.pool_mode == 'align':
+            args.append(0 if feat.code == L.F16 else 1)   # fp16 pipeline: FMA fast path (within 1 fp16 ulp)
+        args.append(L.stream())
         L.check(fn(*args))
         return out
 

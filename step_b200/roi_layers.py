@@ -110,7 +110,7 @@ class _ROIAlign(Function):
             out = torch.empty((R, ph, pw, C), dtype=input.dtype, device=input.device)
             L.check(L.lib().step_roi_align_fwd_nhwc(L.ptr(input), L.dt(input), K, H, W, C, ld, L.ptr(rois), R,
                                                     float(spatial_scale), ph, pw, int(sampling_ratio),
-                                                    L.ptr(out), C, 0, 0, 0, L.stream()))
+                                                    L.ptr(out), C, 0, 0, 0, 1, L.stream()))
             return out.permute(0, 3, 1, 2)
         x = input.detach().to(torch.float32).contiguous()  # ROIAlign_cuda.cu:310 does .contiguous() too
         out = torch.empty((R, C, ph, pw), dtype=torch.float32, device=input.device)

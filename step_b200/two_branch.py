@@ -280,23 +280,32 @@ class TwoBranchNet(nn.Module):
         w2, b2 = _packed(self.downsample2, code)
         lf2 = Act.empty(R * T, 1, ps, ps, self.fc_dim, code, cat.device)
         E.conv(lf, w2, None, b2, lf2, (1, 1, 1), relu=False)
-        wr, br = self._reg_weight("local_reg", code)
-        local_loc = E.linear_small_n(lf2.buf, R * T, D, D, wr, br, 4).view(R, T, 4)
-        # neighbour regressors on the first / last chunk (two_branch.py:265-270)
+        # the three regressors share their input: one pass with the twelve weight rows (two_branch.py:261-270)
         Tc = self.T
         chunks = int(T / Tc)
         half = int(Tc / 2)
         s0, s1 = max(int(Tc / 2) - half, 0), min(int(Tc / 2) + half + 1, T)
         e0 = max((chunks - 1) * Tc + int(Tc / 2) - half, 0)
         e1 = min((chunks - 1) * Tc + int(Tc / 2) + half + 1, T)
-        first = local_loc[:, s0:s1].clone()   # .clone(): the slice may alias local_loc (two_branch.py:265-266)
-        last = local_loc[:, e0:e1].clone()
-        rows_f, rows_l = self._chunk_rows(R, T, s0, s1, e0, e1, cat.device)
-        w1, b1 = self._reg_weight("neighbor_reg1", code)
-        w2n, b2n = self._reg_weight("neighbor_reg2", code)
-        E.linear_small_n(lf2.buf, rows_f.numel(), D, D, w1, b1, 4, y=first.view(-1, 4), accumulate=True, row_map=rows_f)
-        E.linear_small_n(lf2.buf, rows_l.numel(), D, D, w2n, b2n, 4, y=last.view(-1, 4), accumulate=True, row_map=rows_l)
+        w12, b12 = self._reg12(code)
+        local_loc = torch.empty((R, T, 4), dtype=torch.float32, device=cat.device)
+        first = torch.empty((R, s1 - s0, 4), dtype=torch.float32, device=cat.device)
+        last = torch.empty((R, e1 - e0, 4), dtype=torch.float32, device=cat.device)
+        nbytes = L.lib().step_linear_small_n_workspace_bytes(R * T, D, 12)
+        ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=cat.device)
+        L.check(L.lib().step_head_regress(L.ptr(lf2.buf), code, R, T, D, D, L.ptr(w12), L.ptr(b12), s0, s1, e0, e1,
+                                          L.ptr(local_loc), L.ptr(first), L.ptr(last), L.ptr(ws), nbytes, L.stream()))
         return prob, local_loc, first, last
+
+    def _reg12(self, code):
+        """[W_local | W_nb1 | W_nb2] (12 x D, permuted to channels-last) in the compute dtype + fp32 biases."""
+        hw = self._head_weights()
+        k = "w12_%d" % code
+        if k not in hw:
+            w = torch.cat([hw[n + "_w32"] for n in ("local_reg", "neighbor_reg1", "neighbor_reg2")], 0)
+            hw[k] = w.to(E.torch_dtype(code)).contiguous()
+            hw["b12"] = torch.cat([hw[n + "_b"] for n in ("local_reg", "neighbor_reg1", "neighbor_reg2")]).contiguous()
+        return hw[k], hw["b12"]
 
     def _chunk_rows(self, R, T, s0, s1, e0, e1, device):
         """row indices (into [R*T']) of the first / last chunk frames; cached per shape."""

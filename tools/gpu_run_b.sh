@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m step_b200.build > gpurun_out/build.log 2>&1 || { cat gpurun_out/build.log; exit 1; }
+timeout 600 python -m pytest tests -q -m gpu --tb=short -x 2>&1 | tail -4
+python bench.py --steps 20 --warmup 5 --skip-cpu > gpurun_out/y_bench.log 2>&1; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/y_bench.log').read().strip().splitlines()[-1])
+print("clips/s", d["value"], "e2e", d["e2e"]["value"], "roof", d["roofline"]["achieved"], d["roofline"]["ms_per_step_in_kernel"])
+PY
+python tools/microbench.py 2>/dev/null | grep -E "C3_roi|ms|frac_of_hbm|exact|max_rel" | head -30
