@@ -82,8 +82,9 @@ int step_roi_pool_bwd_nchw_f32(const float* grad_out, const int32_t* argmax, con
  * Frame map: ROI column 0 indexes frames of the slice conv_feat[:, t_start:t_start+roi_T]
  * (utils/utils.py:48); with roi_T > 0 the kernel reads frame (f / roi_T) * feat_T + t_start + f % roi_T
  * of the full map instead of needing the slice copied.  roi_T == 0: identity.
- * exact != 0: reference operation order, bit-identical (always used for f32).  exact == 0 with f16 storage:
- * 1/count folded into the tap weights, one fp32 FMA per tap -- within one fp16 ulp of the exact result. */
+ * exact == 1: reference operation order, bit-identical (always used for f32).  f16 storage only: exact == 2:
+ * 1/count folded into the tap weights, one fp32 FMA per tap (within one fp16 ulp of the exact result);
+ * exact == 0: per-pixel merged weights + packed half2 FMAs (a convex combination: a few fp16 ulps). */
 int step_roi_align_fwd_nhwc(const void* feat, int dtype, int K, int H, int W, int C, int feat_ld,
                             const float* rois, int R, float scale, int ph, int pw, int sampling_ratio,
                             void* out, int out_ld, int roi_T, int feat_T, int t_start, int exact,

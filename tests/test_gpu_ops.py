@@ -185,3 +185,27 @@ def test_tube_update_fused_matches_oracle_composition(mode):
     idx = (clip[:, None] * Lo + np.arange(Lo)[None, :]).astype(np.float32)
     exp_flat = np.concatenate([idx[:, :, None], prop], 2)
     assert np.array_equal(fo.cpu().numpy(), exp_flat)
+
+
+def test_roi_align_fp16_fast_paths_within_tolerance():
+    """exact=2 (fp32 FMA) and exact=0 (merged taps, packed half2) against the exact fp16 kernel."""
+    from step_b200 import _lib as L
+    rs = np.random.RandomState(8)
+    K, H, W, C = 5, 14, 14, 64
+    feat = torch.from_numpy(rs.randn(K, H, W, C).astype(np.float32)).cuda().half()
+    R = 400
+    x1 = rs.uniform(-20, 200, R); y1 = rs.uniform(-20, 200, R)
+    rois_np = np.stack([rs.randint(0, K, R), x1, y1, x1 + rs.uniform(0, 230, R), y1 + rs.uniform(0, 230, R)], 1).astype(np.float32)
+    rois_np[:8, 3:] = rois_np[:8, 1:3] + 900.0          # huge ROIs: sampling grid > 3x3 -> per-ROI fallback
+    rois = torch.from_numpy(rois_np).cuda()
+    outs = {}
+    for mode in (1, 2, 0):
+        o = torch.empty((R, 7, 7, C), dtype=torch.float16, device="cuda")
+        L.check(L.lib().step_roi_align_fwd_nhwc(L.ptr(feat), L.F16, K, H, W, C, C, L.ptr(rois), R, 1 / 16., 7, 7, 0,
+                                                L.ptr(o), C, 0, 0, 0, mode, L.stream()))
+        outs[mode] = o.float().cpu().numpy()
+    ref = oops.roi_align_fwd(feat.float().cpu().numpy().transpose(0, 3, 1, 2), rois_np, 1 / 16., 7, 7, 0).transpose(0, 2, 3, 1)
+    assert np.array_equal(outs[1], ref.astype(np.float16).astype(np.float32))
+    mx = np.abs(ref).max()
+    assert np.abs(outs[2] - ref).max() <= 1.5e-3 * mx          # <= 1 fp16 ulp of the largest value
+    assert np.abs(outs[0] - ref).max() <= 6e-3 * mx            # packed half2: a few fp16 ulps

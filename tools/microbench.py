@@ -53,7 +53,7 @@ rois = torch.from_numpy(rois_np).cuda()
 R = rois.shape[0]
 g = torch.Generator().manual_seed(1234)
 feat32 = torch.randn(64, 14, 14, 832, generator=g).cuda()
-for name, code, feat, exact in (("fp32", L.F32, feat32, 1), ("fp16", L.F16, feat32.half(), 1), ("fp16_fma", L.F16, feat32.half(), 0)):
+for name, code, feat, exact in (("fp32", L.F32, feat32, 1), ("fp16", L.F16, feat32.half(), 1), ("fp16_fma", L.F16, feat32.half(), 2), ("fp16_packed", L.F16, feat32.half(), 0)):
     o = torch.empty((R, 7, 7, 832), dtype=feat.dtype, device="cuda")
 
     def run():
