@@ -43,6 +43,7 @@ struct ConvGeom {
   int BN, n_tiles;              // N tile (multiple of 16) and count
   int n_stages;                 // smem pipeline depth used by the one-tile-per-CTA kernel
   int n_stages_p, mh, tmem_bufs;  // persistent kernel: pipeline depth, 128-row halves per tile, accumulator sets
+  int res_tma;                    // residual tile fetched by TMA into shared memory (LINEAR mode, BN % 64 == 0)
   int n_splits, split[2], ld_extra[2], coff_extra[2];  // fused 1x1x1 layers: extra destinations by column range
   __half* y_extra[2];
   int Cout, out_ld, out_coff, res_ld, res_coff, relu;
@@ -354,7 +355,6 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreadsP = 64 + kEpiWarps * 32;     // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
 constexpr int kMaxBNP = 256;
 constexpr int kSlabChunk = 32;                     // columns staged per pass by an epilogue warp
-constexpr int kResPrefetch = 16;                   // 16-byte residual chunks (= 128 columns) prefetched per row
 constexpr int kSlabPitch = kSlabChunk * 2 + 16;    // 80 B: odd multiple of 16 -> conflict-free 16-byte stores
 constexpr int kBookBytesP = 4096 + 4 * 2 * kMaxBNP * 4;           // barriers (first 4 KB) + [tile & 3][scale|shift][BN]
 
@@ -382,8 +382,9 @@ __device__ __forceinline__ HalfOrigin half_origin(const ConvGeom& g, int m_tile)
 
 template <int BK, bool kHasRes>
 __global__ void __launch_bounds__(kThreadsP, 1)
-conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvGeom g,
-                         int total_tiles, const float* __restrict__ scale, const float* __restrict__ shift,
+conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const __grid_constant__ CUtensorMap map_r, ConvGeom g, int total_tiles,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
                          const __half* __restrict__ residual, __half* __restrict__ y) {
   constexpr int kABytes = kBM * BK * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -391,13 +392,19 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   uint64_t* empty_bar = full_bar + kMaxStagesP;
   uint64_t* tfull_bar = empty_bar + kMaxStagesP;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
-  uint32_t* tmem_ptr_s = (uint32_t*)(tempty_bar + 2);
+  uint64_t* rfull_bar = tempty_bar + 2;            // [2] residual tile landed (TMA)
+  uint64_t* rempty_bar = rfull_bar + 2;            // [2] residual tile consumed by all epilogue warps
+  uint32_t* tmem_ptr_s = (uint32_t*)(rempty_bar + 2);
   float* ss_all = (float*)(smem_raw + 4096);       // [tile & 3][scale | shift][kMaxBNP]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + kBookBytesP + 1023) & ~(uintptr_t)1023);
   const int mh = g.mh;
   const int b_bytes = g.BN * BK * 2;
   const int stage_bytes = mh * kABytes + b_bytes;  // multiple of 1024 (BN % 16 == 0)
   uint8_t* slabs = smem + (size_t)g.n_stages_p * stage_bytes;   // [kEpiWarps][32 rows][kSlabPitch]
+  // residual tiles (kHasRes && g.res_tma): [2 buffers][BN/64 boxes][128 rows x 128 B, 128B-swizzled], 1024-aligned
+  uint8_t* rbuf = (uint8_t*)(((uintptr_t)(slabs + (size_t)kEpiWarps * 32 * kSlabPitch) + 1023) & ~(uintptr_t)1023);
+  const bool res_tma = kHasRes && g.res_tma;
+  const int res_boxes = g.BN >> 6;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = g.taps * g.kblocks_per_tap;
@@ -407,7 +414,11 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < g.n_stages_p; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiWarps); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiWarps);
+      mbar_init(&rfull_bar[b], 1); mbar_init(&rempty_bar[b], kEpiWarps);
+    }
+    if (kHasRes) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
     fence_barrier_init();
   }
   uint32_t ncols = 32;
@@ -427,9 +438,18 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     if (elect_one()) {
       const uint32_t tx_bytes = (uint32_t)(mh * g.a_bytes + b_bytes);
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int pit = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++pit) {
         const int mt = tile / g.n_tiles;
         const int n0 = (tile - mt * g.n_tiles) * g.BN;
+        if (res_tma) {
+          // residual tile of this output tile (two_branch.py:79-81): coalesced, asynchronous, swizzled like an operand
+          const int rb = pit & 1;
+          mbar_wait(&rempty_bar[rb], (((uint32_t)pit >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&rfull_bar[rb], (uint32_t)(res_boxes * kBM * 128));
+          for (int j = 0; j < res_boxes; ++j)
+            tma_load_2d(&map_r, &rfull_bar[rb], rbuf + ((size_t)rb * res_boxes + j) * (kBM * 128), n0 + j * 64, mt * kBM);
+        }
         HalfOrigin ho[2];
         int iw[2], ih[2], it[2], in_[2];
         for (int h = 0; h < mh; ++h) {
@@ -540,33 +560,28 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         s_scale[i] = (scale && c < g.Cout) ? scale[c] : 1.0f;
         s_shift[i] = (shift && c < g.Cout) ? shift[c] : 0.0f;
       }
-      // Residual (two_branch.py:79-81): the row-strided 16-byte loads of this warp's first 128 columns are issued
-      // before waiting for the accumulator so their latency overlaps the MMAs of this tile.
-      uint4 rpre[kResPrefetch];
-      if (kHasRes) {
-        const __half* rr0 = pix >= 0 ? residual + (size_t)pix * g.res_ld + g.res_coff + nbase : nullptr;
-#pragma unroll
-        for (int j = 0; j < kResPrefetch; ++j) {
-          rpre[j] = make_uint4(0, 0, 0, 0);
-          if (rr0 && j * 8 < ncol && nbase + j * 8 < g.Cout) rpre[j] = *reinterpret_cast<const uint4*>(rr0 + j * 8);
-        }
-      }
       __syncwarp();
       mbar_wait(&tfull_bar[buf], use & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * mh + hsel) * ncols + (uint32_t)col0;
       const __half* rrow = (kHasRes && pix >= 0) ? residual + (size_t)pix * g.res_ld + g.res_coff + nbase : nullptr;
+      const uint8_t* rtile = rbuf + (size_t)(it & 1) * res_boxes * (kBM * 128);
+      if (res_tma) mbar_wait(&rfull_bar[it & 1], ((uint32_t)it >> 1) & 1u);
       for (int cb = 0; cb < ncol; cb += kSlabChunk) {
         const int cw = min(kSlabChunk, ncol - cb);   // 16 or 32 columns in this pass
         uint4 rreg[kSlabChunk / 8];
         if (kHasRes) {
 #pragma unroll
           for (int j = 0; j < kSlabChunk / 8; ++j) {
-            const int pj = cb / 8 + j;               // 16-byte chunk index within this warp's columns
-            if (pj < kResPrefetch) rreg[j] = rpre[pj];
-            else {
-              rreg[j] = make_uint4(0, 0, 0, 0);
-              if (rrow && j * 8 < cw && nbase + cb + j * 8 < g.Cout) rreg[j] = *reinterpret_cast<const uint4*>(rrow + cb + j * 8);
+            rreg[j] = make_uint4(0, 0, 0, 0);
+            if (res_tma) {
+              // tile-relative column -> 64-column box, 16-byte chunk inside the 128-byte row, XOR-swizzled by row
+              const int tc = col0 + cb + j * 8;
+              if (j * 8 < cw)
+                rreg[j] = *reinterpret_cast<const uint4*>(rtile + (size_t)(tc >> 6) * (kBM * 128) + row * 128 +
+                                                          ((((tc & 63) >> 3) ^ (row & 7)) << 4));
+            } else if (rrow && j * 8 < cw && nbase + cb + j * 8 < g.Cout) {
+              rreg[j] = *reinterpret_cast<const uint4*>(rrow + cb + j * 8);
             }
           }
         }
@@ -628,6 +643,10 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      }
+      if (res_tma) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rempty_bar[it & 1]);
       }
     }
   }
@@ -738,7 +757,7 @@ static int conv_variant() {
 }
 
 struct ConvPlan {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_r;
   ConvGeom g;
   int BK;
   size_t smem_bytes;
@@ -773,7 +792,7 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   const bool persist = conv_variant() == 3 || (conv_variant() == 2 && taps == 1);
   {
     // N tile: as wide as the accumulator allows -- every N tile re-reads the whole A operand through L2.
-    const int cap = persist ? kMaxBNP : (p->residual ? kMaxBNRes : kMaxBN);
+    const int cap = (persist && !p->residual) ? kMaxBNP : (p->residual ? kMaxBNRes : kMaxBN);
     g.n_tiles = (p->Cout + cap - 1) / cap;
     g.BN = (((p->Cout + g.n_tiles - 1) / g.n_tiles) + 15) / 16 * 16;
     g.n_stages = g.BN > 128 ? 2 : 3;
@@ -871,14 +890,28 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
     int ncols = 32;
     while (ncols < g.BN) ncols <<= 1;
     g.tmem_bufs = (g.mh * ncols * 2 <= 512) ? 2 : 1;
-    const size_t budget = 227 * 1024 - kBookBytesP - 1024 - (size_t)kEpiWarps * 32 * kSlabPitch;
+    g.res_tma = (persist && p->residual && g.mh == 1 && mode == A_LINEAR && g.BN % 64 == 0 && p->Cout % 64 == 0) ? 1 : 0;
+    const size_t res_bytes = g.res_tma ? (size_t)2 * (g.BN / 64) * kBM * 128 + 1024 : 0;
+    const size_t budget = 227 * 1024 - kBookBytesP - 1024 - (size_t)kEpiWarps * 32 * kSlabPitch - res_bytes;
     const size_t stage_bytes = (size_t)g.mh * kBM * BK * 2 + (size_t)g.BN * BK * 2;
     int st = (int)(budget / stage_bytes);
     g.n_stages_p = st > kMaxStagesP ? kMaxStagesP : st;
     if (const char* e = getenv("STEP_B200_STAGES")) { int v = atoi(e); if (v >= 2 && v < g.n_stages_p) g.n_stages_p = v; }
     STEP_CHECK_ARG(g.n_stages_p >= 2, "conv3d(f16): tile does not fit shared memory");
     pl->persist_tiles = (int)(((m128 + g.mh - 1) / g.mh) * g.n_tiles);
-    pl->persist_smem = kBookBytesP + 1024 + (size_t)g.n_stages_p * stage_bytes + (size_t)kEpiWarps * 32 * kSlabPitch;
+    pl->persist_smem = kBookBytesP + 1024 + (size_t)g.n_stages_p * stage_bytes + (size_t)kEpiWarps * 32 * kSlabPitch + res_bytes;
+    if (g.res_tma) {
+      cuuint64_t rdims[2] = {(cuuint64_t)p->Cout, (cuuint64_t)g.M};
+      cuuint64_t rstr[1] = {(cuuint64_t)p->res_ld * 2};
+      cuuint32_t rbox[2] = {64, (cuuint32_t)kBM};
+      const cuuint32_t ones2[2] = {1, 1};
+      CUresult cr2 = g_encode_tiled(&pl->map_r, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)((const __half*)p->residual + p->res_coff),
+                                    rdims, rstr, rbox, ones2, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr2 != CUDA_SUCCESS) return fail(STEP_E_DRIVER, "conv3d(f16): tensor map (residual) encode failed: CUresult %d", (int)cr2);
+    } else {
+      pl->map_r = pl->map_b;   // unused placeholder
+    }
   }
   return 0;
 }
@@ -907,7 +940,7 @@ static int launch_persist(const ConvPlan& pl, const step_conv_params* p, cudaStr
   }
   const int total = pl.persist_tiles;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  conv_umma_persist_kernel<BK, kHasRes><<<grid, kThreadsP, pl.persist_smem, s>>>(pl.map_a, pl.map_b, pl.g, total, p->scale,
+  conv_umma_persist_kernel<BK, kHasRes><<<grid, kThreadsP, pl.persist_smem, s>>>(pl.map_a, pl.map_b, pl.map_r, pl.g, total, p->scale,
                                                                                 p->shift, (const __half*)p->residual,
                                                                                 (__half*)p->y);
   STEP_LAUNCH_CHECK("conv_umma_persist_kernel");

@@ -7,4 +7,4 @@ import json
 d=json.loads(open('gpurun_out/y_bench.log').read().strip().splitlines()[-1])
 print("clips/s", d["value"], "e2e", d["e2e"]["value"], "roof", d["roofline"]["achieved"], d["roofline"]["ms_per_step_in_kernel"])
 PY
-python tools/microbench.py 2>/dev/null | grep -E "C3_roi|ms|frac_of_hbm|exact|max_rel" | head -30
+python tools/conv_bench.py loc_res loc_1088 loc_1024 2>&1 | tail -3
