@@ -44,6 +44,7 @@ struct ConvGeom {
   int n_stages;                 // smem pipeline depth used by the one-tile-per-CTA kernel
   int n_stages_p, mh, tmem_bufs;  // persistent kernel: pipeline depth, 128-row halves per tile, accumulator sets
   int res_tma;                    // residual tile fetched by TMA into shared memory (LINEAR mode, BN % 64 == 0)
+  int cluster;                    // 1, or 2: CTA pairs sharing the weight tile by TMA multicast
   int n_splits, split[2], ld_extra[2], coff_extra[2];  // fused 1x1x1 layers: extra destinations by column range
   __half* y_extra[2];
   int Cout, out_ld, out_coff, res_ld, res_coff, relu;
@@ -362,6 +363,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d_mcast(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                                  uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6}], [%2], %3;"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 struct HalfOrigin {
   long long m0;            // first output pixel (linear) of this 128-row half (LINEAR / IM2COL)
   int bn, bt0, bh0, bw0;   // BOX origin
@@ -383,7 +403,8 @@ __device__ __forceinline__ HalfOrigin half_origin(const ConvGeom& g, int m_tile)
 template <int BK, bool kHasRes>
 __global__ void __launch_bounds__(kThreadsP, 1)
 conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         const __grid_constant__ CUtensorMap map_r, ConvGeom g, int total_tiles,
+                         const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_bh, ConvGeom g,
+                         int total_tiles,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const __half* __restrict__ residual, __half* __restrict__ y) {
   constexpr int kABytes = kBM * BK * 2;
@@ -409,11 +430,18 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = g.taps * g.kblocks_per_tap;
   const int nbuf = g.tmem_bufs;                    // 1 or 2 accumulator sets
+  // Cluster of 2 CTAs (two neighbouring SMs) on adjacent M tiles of the same N tile: each CTA fetches half of the
+  // weight tile and TMA-multicasts it into both CTAs' shared memory, so the weight traffic out of L2 -- the larger
+  // share for wide-N 1x1x1 layers -- is halved.  A stage may only be refilled when BOTH consumers released it.
+  const bool cl2 = g.cluster == 2;
+  const uint32_t crank = cl2 ? cluster_ctarank() : 0;
+  const int tile_step = cl2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tile_first = cl2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-    for (int s = 0; s < g.n_stages_p; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < g.n_stages_p; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], cl2 ? 2 : 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiWarps);
       mbar_init(&rfull_bar[b], 1); mbar_init(&rempty_bar[b], kEpiWarps);
@@ -430,8 +458,14 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (cl2) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+
+  // tile -> (m tile, n offset).  In a cluster the two CTAs take M tiles 2*pm and 2*pm+1 of the same N tile (the odd
+  // one may lie past the end: its loads are zero-filled and nothing is stored, but it still runs the k loop).
+  auto tile_mt = [&](int tile) { const int pm = tile / g.n_tiles; return cl2 ? pm * 2 + (int)crank : pm; };
+  auto tile_n0 = [&](int tile) { return (tile % g.n_tiles) * g.BN; };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -439,9 +473,9 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       const uint32_t tx_bytes = (uint32_t)(mh * g.a_bytes + b_bytes);
       int stage = 0; uint32_t phase = 0;
       int pit = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++pit) {
-        const int mt = tile / g.n_tiles;
-        const int n0 = (tile - mt * g.n_tiles) * g.BN;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++pit) {
+        const int mt = tile_mt(tile);
+        const int n0 = tile_n0(tile);
         if (res_tma) {
           // residual tile of this output tile (two_branch.py:79-81): coalesced, asynchronous, swizzled like an operand
           const int rb = pit & 1;
@@ -479,7 +513,13 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                                    (uint16_t)kh, (uint16_t)kt);
               }
             }
-            tma_load_3d(&map_b, &full_bar[stage], st + mh * kABytes, c0, tap, n0);
+            if (cl2) {
+              const int hb = b_bytes >> 1;   // my half of the weight rows, delivered to both CTAs
+              tma_load_3d_mcast(&map_bh, &full_bar[stage], st + mh * kABytes + crank * hb, c0, tap, n0 + (int)crank * (g.BN >> 1),
+                                (uint16_t)3);
+            } else {
+              tma_load_3d(&map_b, &full_bar[stage], st + mh * kABytes, c0, tap, n0);
+            }
             if (++stage == g.n_stages_p) { stage = 0; phase ^= 1; }
           }
         }
@@ -489,7 +529,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     // ===================== MMA issuer =====================
     int stage = 0; uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
       const int buf = nbuf == 2 ? (it & 1) : 0;
       const uint32_t use = (uint32_t)(nbuf == 2 ? (it >> 1) : it);
       mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // the epilogue has drained this accumulator set
@@ -508,7 +548,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
               umma_f16(tmem_d + (uint32_t)h * ncols, make_smem_desc<BK>(a_addr + k * 32), make_smem_desc<BK>(b_addr + k * 32),
                        g.idesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (cl2) umma_commit_mcast(&empty_bar[stage], (uint16_t)3); else umma_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) umma_commit(&tfull_bar[buf]);
         }
         __syncwarp();
@@ -543,11 +583,11 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       return m < g.M ? m : -1;
     };
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
       const int buf = nbuf == 2 ? (it & 1) : 0;
       const uint32_t use = (uint32_t)(nbuf == 2 ? (it >> 1) : it);
-      const int mt = tile / g.n_tiles;
-      const int n0 = (tile - mt * g.n_tiles) * g.BN;
+      const int mt = tile_mt(tile);
+      const int n0 = tile_n0(tile);
       const long long pix = row_pixel(mt * mh + hsel);
       const int nbase = n0 + col0;                 // first output channel this warp handles
       // per-channel epilogue constants of this tile; warps of the same tile write identical values into
@@ -652,6 +692,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (cl2) cluster_sync_all();   // do not exit while the peer may still multicast into / signal this CTA
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(alloc_cols) : "memory");
@@ -757,7 +798,7 @@ static int conv_variant() {
 }
 
 struct ConvPlan {
-  CUtensorMap map_a, map_b, map_r;
+  CUtensorMap map_a, map_b, map_r, map_bh;
   ConvGeom g;
   int BK;
   size_t smem_bytes;
@@ -898,7 +939,24 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
     g.n_stages_p = st > kMaxStagesP ? kMaxStagesP : st;
     if (const char* e = getenv("STEP_B200_STAGES")) { int v = atoi(e); if (v >= 2 && v < g.n_stages_p) g.n_stages_p = v; }
     STEP_CHECK_ARG(g.n_stages_p >= 2, "conv3d(f16): tile does not fit shared memory");
-    pl->persist_tiles = (int)(((m128 + g.mh - 1) / g.mh) * g.n_tiles);
+    g.cluster = 1;
+    {
+      const char* e = getenv("STEP_B200_CLUSTER");
+      const bool want = e ? (e[0] == '2') : true;
+      if (want && persist && g.mh == 1 && m128 >= 2 * 74 && g.BN >= 64 && (g.BN / 2) % 8 == 0) g.cluster = 2;
+    }
+    pl->persist_tiles = g.cluster == 2 ? (int)(((m128 + 1) / 2) * g.n_tiles) : (int)(((m128 + g.mh - 1) / g.mh) * g.n_tiles);
+    pl->map_bh = pl->map_b;
+    if (g.cluster == 2) {
+      cuuint64_t bdims[3] = {(cuuint64_t)p->Cin, (cuuint64_t)taps, (cuuint64_t)p->Cout};
+      cuuint64_t bstr[2] = {(cuuint64_t)p->w_ld * 2, (cuuint64_t)taps * p->w_ld * 2};
+      cuuint32_t bbox[3] = {(cuuint32_t)BK, 1, (cuuint32_t)(g.BN / 2)};
+      const cuuint32_t ones3[3] = {1, 1, 1};
+      CUresult cr3 = g_encode_tiled(&pl->map_bh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)p->w, bdims, bstr, bbox, ones3,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(BK), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr3 != CUDA_SUCCESS) return fail(STEP_E_DRIVER, "conv3d(f16): tensor map (B half) encode failed: CUresult %d", (int)cr3);
+    }
     pl->persist_smem = kBookBytesP + 1024 + (size_t)g.n_stages_p * stage_bytes + (size_t)kEpiWarps * 32 * kSlabPitch + res_bytes;
     if (g.res_tma) {
       cuuint64_t rdims[2] = {(cuuint64_t)p->Cout, (cuuint64_t)g.M};
@@ -939,10 +997,23 @@ static int launch_persist(const ConvPlan& pl, const step_conv_params* p, cudaStr
     attr_set = true;
   }
   const int total = pl.persist_tiles;
-  const int grid = total < kNumSMs ? total : kNumSMs;
-  conv_umma_persist_kernel<BK, kHasRes><<<grid, kThreadsP, pl.persist_smem, s>>>(pl.map_a, pl.map_b, pl.map_r, pl.g, total, p->scale,
-                                                                                p->shift, (const __half*)p->residual,
-                                                                                (__half*)p->y);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  if (pl.g.cluster == 2) {
+    const int pairs = total < kNumSMs / 2 ? total : kNumSMs / 2;
+    cfg.gridDim = dim3(2 * pairs);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(total < kNumSMs ? total : kNumSMs);
+  }
+  cfg.blockDim = dim3(kThreadsP);
+  cfg.dynamicSmemBytes = pl.persist_smem;
+  cfg.stream = s;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_umma_persist_kernel<BK, kHasRes>, pl.map_a, pl.map_b, pl.map_r, pl.map_bh, pl.g,
+                                      total, p->scale, p->shift, (const __half*)p->residual, (__half*)p->y);
+  if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "conv_umma_persist_kernel launch: %s", cudaGetErrorString(le)); }
   STEP_LAUNCH_CHECK("conv_umma_persist_kernel");
   return 0;
 }
