@@ -942,7 +942,9 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
     g.cluster = 1;
     {
       const char* e = getenv("STEP_B200_CLUSTER");
-      const bool want = e ? (e[0] == '2') : true;
+      // measured (tools/conv_bench.py, STEP_B200_CLUSTER=1|2): no gain on B200 -- the wide-N 1x1x1 layers are not
+      // bound by the weight traffic out of L2 -- so the multicast path is opt-in (validated by tests/test_gpu_conv.py)
+      const bool want = e ? (e[0] == '2') : false;
       if (want && persist && g.mh == 1 && m128 >= 2 * 74 && g.BN >= 64 && (g.BN / 2) % 8 == 0) g.cluster = 2;
     }
     pl->persist_tiles = g.cluster == 2 ? (int)(((m128 + 1) / 2) * g.n_tiles) : (int)(((m128 + g.mh - 1) / g.mh) * g.n_tiles);

@@ -282,3 +282,20 @@ def test_fused_1x1_multi_destination_matches_separate_convs():
         off += c
     assert float(big[..., :64].abs().max()) == 0 and float(big[..., 64 + outs[0]:].abs().max()) == 0
     assert float(t2[..., :8].abs().max()) == 0
+
+
+def test_cluster_multicast_variant_matches(monkeypatch):
+    """STEP_B200_CLUSTER=2: CTA pairs share the weight tile through TMA multicast (opt-in path)."""
+    g = torch.Generator().manual_seed(21)
+    N, T, H, W, Cin, Cout = 3, 8, 28, 28, 192, 448       # 18816 pixels = 147 M tiles -> below the 148 threshold
+    x = torch.randn(8, 8, 28, 28, Cin, generator=g).half().cuda()   # 50176 pixels = 392 M tiles -> clusters of 2
+    w = (torch.randn(Cout, Cin, 1, 1, 1, generator=g) / Cin ** 0.5).half()
+    scale = (torch.rand(Cout, generator=g) + 0.5).cuda()
+    shift = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(8, 8, 28, 28, Cout, generator=g).half().cuda()
+    outs = {}
+    for mode in ("1", "2"):
+        monkeypatch.setenv("STEP_B200_CLUSTER", mode)
+        outs[mode] = (run_conv(x, w, L.F16, (1, 1, 1), (1, 1, 1), scale, shift, True, None, L.A_AUTO).float(),
+                      run_conv(x, w, L.F16, (1, 1, 1), (1, 1, 1), scale, shift, True, res, L.A_AUTO).float())
+    assert torch.equal(outs["1"][0], outs["2"][0]) and torch.equal(outs["1"][1], outs["2"][1])

@@ -209,3 +209,33 @@ def test_roi_align_fp16_fast_paths_within_tolerance():
     mx = np.abs(ref).max()
     assert np.abs(outs[2] - ref).max() <= 1.5e-3 * mx          # <= 1 fp16 ulp of the largest value
     assert np.abs(outs[0] - ref).max() <= 6e-3 * mx            # packed half2: a few fp16 ulps
+
+
+def test_detect_postprocess_matches_reference_loop():
+    """Segmented on-device post-processing == the per-clip x per-class loop of test.py:156-218."""
+    from oracle import postprocess as opp
+    from step_b200 import postprocess as pp
+    rs = np.random.RandomState(12)
+    nums = [11, 11, 11]
+    R, ncls, T = sum(nums), 60, 4
+    prob = rs.rand(R, ncls).astype(np.float32) ** 3
+    ctr = rs.uniform(40, 180, (R, 2)).astype(np.float32)
+    wh = rs.uniform(20, 120, (R, 2)).astype(np.float32)
+    box = np.concatenate([ctr - wh / 2, ctr + wh / 2], 1).astype(np.float32)
+    box[3] = [50, 50, 51, 120]                                   # degenerate -> whole 400x400 image in valid_tubes
+    loc = np.tile(box[:, None, :], (1, T, 1)) + rs.randn(R, T, 4).astype(np.float32)
+    loc[:, T // 2] = box
+    det = pp.detect(cu(np.tile(prob[:, None, :], (1, T, 1))), cu(loc), nums, 0.2, 0.4, 224.0, 224.0, topk=0)
+    got = pp.to_lists(det, len(nums))
+    ref = opp.detections(prob, box, nums, 0.2, 0.4, 224.0, 224.0, topk=0)
+    for g, r in zip(got, ref):
+        assert len(g) == len(r) and len(r) > 20
+        gs = sorted((c, round(s, 6), tuple(np.round(b, 5))) for b, c, s in g)
+        rs_ = sorted((c, round(s, 6), tuple(np.round(b, 5))) for b, c, s in r)
+        assert gs == rs_
+    # top-k per clip keeps exactly the k best kept scores
+    det = pp.detect(cu(prob), cu(loc), nums, 0.2, 0.4, 224.0, 224.0, topk=10)
+    got = pp.to_lists(det, len(nums))
+    ref = opp.detections(prob, box, nums, 0.2, 0.4, 224.0, 224.0, topk=10)
+    for g, r in zip(got, ref):
+        assert [round(s, 6) for _, _, s in g] == [round(s, 6) for _, _, s in r]
