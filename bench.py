@@ -363,7 +363,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying the CUDA graph")
-    ap.add_argument("--inflight", type=int, default=2, help="independent batches kept in flight on separate streams")
+    ap.add_argument("--inflight", type=int, default=3, help="independent batches kept in flight on separate streams")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
