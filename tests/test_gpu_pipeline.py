@@ -134,3 +134,42 @@ def test_reference_style_driver_calls():
     dec = step_b200.tube_utils.decode_coef(flat.view(-1, 5)[:, 1:].contiguous(), loc.view(-1, 4))
     assert torch.allclose(dec.view(loc.shape), hist[0]["pred_loc"], atol=0.5)
     assert l0.numel() == 1 and float(l0) == 0.0
+
+
+def test_full_size_c4_properties():
+    """BASELINE.json config 4 at full size (B=8, T=32, 224x224, 11 proposals, 3 steps), size-independent
+    properties: (1) determinism; (2) the CUDA-graph replay equals the eager launch sequence bit for bit;
+    (3) clips are independent units -- the first 4 clips run alone reproduce their rows of the 8-clip batch
+    bit for bit (what makes the clip-parallel multi-GPU sharding exact); (4) per-class NMS on the result is
+    idempotent and keeps ascending indices."""
+    import step_b200
+    from step_b200.roi_layers import nms
+    cfg = synth.make_cfg(fp16=True, T=8, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 1}, image_size=(224, 224))
+    nets = build(cfg)
+    B, N = 8, 11
+    x = synth.make_clips(B, 32, 224, 224).cuda()
+    tubes = synth.make_proposals(B, N, cfg.T, 224, 224)
+
+    def eager(xx, tb):
+        with torch.no_grad():
+            cf = nets["base_net"](xx)
+            h, _ = step_b200.inference(cfg, cf, None, nets, cfg.max_iter, tb, want_trajectory=False)
+        return [(d["pred_prob"][:, 0].clone(), d["pred_loc"].clone()) for d in h]
+
+    a, b = eager(x, tubes), eager(x, tubes)
+    for (p0, l0), (p1, l1) in zip(a, b):
+        assert torch.equal(p0, p1) and torch.equal(l0, l1)                      # (1)
+    runner = step_b200.StepRunner(cfg, nets, B, 32, 224, 224, tubes)
+    g = [(d["pred_prob"][:, 0].clone(), d["pred_loc"].clone()) for d in runner(x)]
+    g2 = [(d["pred_prob"][:, 0].clone(), d["pred_loc"].clone()) for d in runner(x)]
+    for (p0, l0), (p1, l1), (p2, l2) in zip(a, g, g2):
+        assert torch.equal(p0, p1) and torch.equal(l0, l1) and torch.equal(p1, p2) and torch.equal(l1, l2)   # (2)
+    half = eager(x[:4].contiguous(), tubes[:4])
+    for (p0, l0), (ph, lh) in zip(a, half):
+        assert torch.equal(p0[:4 * N], ph) and torch.equal(l0[:4 * N], lh)      # (3)
+    assert all(torch.isfinite(p).all() and torch.isfinite(l).all() for p, l in a)
+    prob, loc = a[-1]
+    boxes = loc[:N, cfg.T // 2].contiguous()
+    keep = nms(boxes, prob[:N, 0].contiguous(), 0.4)
+    again = nms(boxes[keep], prob[:N, 0][keep].contiguous(), 0.4)
+    assert torch.equal(again.cpu(), torch.arange(keep.numel())) and bool((keep[1:] > keep[:-1]).all())   # (4)
