@@ -13,7 +13,6 @@ namespace step {
 // outputs then hit the same few KB in L1 instead of re-reading L2 27 times (the pools of
 // Mixed.branch_3, i3dpt.py:150-153, are 3x3x3 / stride 1).  Padded cells hold 0 (ConstantPad3d), cells
 // beyond the padded extent (ceil_mode overhang) are ignored.
-constexpr int kPoolCV = 4;
 template <typename T> __device__ __forceinline__ uint4 vec_lowest();
 template <> __device__ __forceinline__ uint4 vec_lowest<float>() {
   const uint32_t v = __float_as_uint(-3.402823466e+38f);
@@ -36,13 +35,17 @@ __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
 template <> __device__ __forceinline__ uint4 vec_max<__half>(uint4 a, uint4 b) {
   return make_uint4(hmax2_u32(a.x, b.x), hmax2_u32(a.y, b.y), hmax2_u32(a.z, b.z), hmax2_u32(a.w, b.w));
 }
-template <typename T>
+// kPoolCV vectors of 16 B per pixel per CTA: 8 (= one full 128-byte line: a 64-byte chunk made two CTAs pull the
+// same DRAM line, 2x read traffic in the ncu capture) when the channel count allows, else 4.
+template <typename T, int CKT, int CKH, int CKW, int kPoolCV>
 __global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ x, int N, int T_, int H, int W, int C,
-                                                        int in_ld, int KT, int KH, int KW, int ST, int SH, int SW,
+                                                        int in_ld, int KT_, int KH_, int KW_, int ST, int SH, int SW,
                                                         int PT, int PH, int PW, int pad_hi_t, int pad_hi_h,
                                                         int pad_hi_w, int OT, int OH, int OW, T* __restrict__ y,
                                                         int out_ld, int TT, int TH, int TW) {
   constexpr int VN = Vec16<T>::N;
+  // compile-time window (fully unrolled: all tap loads are issued back to back) or runtime window (CK* == 0)
+  const int KT = CKT ? CKT : KT_, KH = CKH ? CKH : KH_, KW = CKW ? CKW : KW_;
   const int nvec = C / VN;
   const int tiles_w = (OW + TW - 1) / TW, tiles_h = (OH + TH - 1) / TH, tiles_t = (OT + TT - 1) / TT;
   int r = blockIdx.x;
@@ -59,15 +62,18 @@ __global__ void __launch_bounds__(256) maxpool3d_kernel(const T* __restrict__ x,
     // max is exact in the storage type: stay in packed half2 (4 HMNMX2 per 16-byte load, no converts)
     uint4 m = vec_lowest<T>();
     bool touches_pad = false, any = false;
+#pragma unroll
     for (int kt = 0; kt < KT; ++kt) {
       const int t = ot * ST + kt - PT;          // coordinate in the un-padded tensor
       if (t >= T_ + pad_hi_t) continue;         // beyond the padded extent (ceil_mode overhang)
       const bool tp = (t < 0) || (t >= T_);
+#pragma unroll
       for (int kh = 0; kh < KH; ++kh) {
         const int h = oh * SH + kh - PH;
         if (h >= H + pad_hi_h) continue;
         if (tp || h < 0 || h >= H) { touches_pad = true; continue; }
         const T* rowp = x + (((size_t)n * T_ + t) * H + h) * W * in_ld + cv * VN;
+#pragma unroll
         for (int kw = 0; kw < KW; ++kw) {
           const int w = ow * SW + kw - PW;
           if (w >= W + pad_hi_w) continue;
@@ -166,25 +172,17 @@ __global__ void clip_to_ndhwc_kernel(const float* __restrict__ clip, int N, int 
 // clip [N,T,Cc,H,W] fp32 -> s2d [N,T/2,H/2,W/2,ld] f16, channel ((rt*2+rh)*2+rw)*Cc + c.
 // One CTA per output row (n, t2, h2): the 4*Cc input rows it needs are read coalesced into smem, then
 // each thread emits one 16-byte (8-channel) vector of one output pixel: both sides fully coalesced.
+constexpr int kS2dRows = 8;   // output rows per CTA: amortises the per-thread channel-decode setup (runtime div/mod)
 __global__ void __launch_bounds__(256) clip_to_s2d_kernel(const float* __restrict__ clip, int N, int T_, int Cc, int H,
                                                           int W, __half* __restrict__ out, int ld) {
   extern __shared__ float rows[];  // [rt][rh][c][W]
   const int T2 = T_ / 2, H2 = H / 2, W2 = W / 2;
+  const int hblocks = (H2 + kS2dRows - 1) / kS2dRows;
   int r = blockIdx.x;
-  const int h2 = r % H2; r /= H2;
+  const int hb = r % hblocks; r /= hblocks;
   const int t2 = r % T2;
   const int n = r / T2;
-  // 4*Cc input rows, each W contiguous floats: no per-element div/mod (runtime divisors are ~40 instructions)
-  for (int rt = 0; rt < 2; ++rt)
-    for (int rh = 0; rh < 2; ++rh)
-      for (int c = 0; c < Cc; ++c) {
-        const float* src = clip + ((((size_t)n * T_ + 2 * t2 + rt) * Cc + c) * H + 2 * h2 + rh) * W;
-        float* dst = rows + ((rt * 2 + rh) * Cc + c) * W;
-        for (int w = threadIdx.x; w < W; w += blockDim.x) dst[w] = src[w];
-      }
-  __syncthreads();
   const int nvec = ld / 8;
-  __half* orow = out + (((size_t)n * T2 + t2) * H2 + h2) * W2 * ld;
   // thread = (w2, 8-channel vector); channel ch = ((rt*2+rh)*2+rw)*Cc + c  ->  smem row (rt,rh,c), column 2*w2+rw
   const int cvs = threadIdx.x % nvec;          // blockDim.x is a multiple of nvec (ld = 32 -> 4)
   int srow[8], scol[8];
@@ -196,11 +194,26 @@ __global__ void __launch_bounds__(256) clip_to_s2d_kernel(const float* __restric
       srow[k] = ((q >> 1) * Cc + c) * W; scol[k] = q & 1;
     } else { srow[k] = -1; scol[k] = 0; }
   }
-  for (int w2 = threadIdx.x / nvec; w2 < W2; w2 += blockDim.x / nvec) {
-    float v[8];
+  for (int hh = 0; hh < kS2dRows; ++hh) {
+    const int h2 = hb * kS2dRows + hh;
+    if (h2 >= H2) break;
+    // 4*Cc input rows, each W contiguous floats
+    for (int rt = 0; rt < 2; ++rt)
+      for (int rh = 0; rh < 2; ++rh)
+        for (int c = 0; c < Cc; ++c) {
+          const float* src = clip + ((((size_t)n * T_ + 2 * t2 + rt) * Cc + c) * H + 2 * h2 + rh) * W;
+          float* dst = rows + ((rt * 2 + rh) * Cc + c) * W;
+          for (int w = threadIdx.x; w < W; w += blockDim.x) dst[w] = src[w];
+        }
+    __syncthreads();
+    __half* orow = out + (((size_t)n * T2 + t2) * H2 + h2) * W2 * ld;
+    for (int w2 = threadIdx.x / nvec; w2 < W2; w2 += blockDim.x / nvec) {
+      float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = srow[k] >= 0 ? rows[srow[k] + 2 * w2 + scol[k]] : 0.0f;
-    store16(orow + (size_t)w2 * ld + cvs * 8, v);
+      for (int k = 0; k < 8; ++k) v[k] = srow[k] >= 0 ? rows[srow[k] + 2 * w2 + scol[k]] : 0.0f;
+      store16(orow + (size_t)w2 * ld + cvs * 8, v);
+    }
+    __syncthreads();
   }
 }
 
@@ -370,15 +383,27 @@ extern "C" int step_maxpool3d_fwd(const void* x, int dtype, int N, int T, int H,
   const int TW = OW < 8 ? OW : (OW % 7 == 0 ? 7 : 8), TH = OH < 8 ? OH : (OH % 7 == 0 ? 7 : 8), TT = OT < 4 ? OT : 4;
   long long tiles = (long long)N * ceil_div(OT, TT) * ceil_div(OH, TH) * ceil_div(OW, TW);
   STEP_CHECK_ARG(tiles < (1LL << 31), "maxpool3d: too many tiles");
-  dim3 grid((unsigned)tiles, ceil_div(C / vn, kPoolCV));
-  if (dtype == STEP_F16)
-    maxpool3d_kernel<__half><<<grid, 256, 0, cu(stream)>>>((const __half*)x, N, T, H, W, C, in_ld, KT, KH, KW, ST, SH, SW,
-                                                           PT, PH, PW, pad_hi_t, pad_hi_h, pad_hi_w, OT, OH, OW,
-                                                           (__half*)y, out_ld, TT, TH, TW);
-  else
-    maxpool3d_kernel<float><<<grid, 256, 0, cu(stream)>>>((const float*)x, N, T, H, W, C, in_ld, KT, KH, KW, ST, SH, SW, PT,
-                                                          PH, PW, pad_hi_t, pad_hi_h, pad_hi_w, OT, OH, OW, (float*)y,
-                                                          out_ld, TT, TH, TW);
+  const bool cv8 = (C / vn) % 8 == 0 && ((uintptr_t)x & 127) == 0 && (in_ld * (dtype == STEP_F16 ? 2 : 4)) % 128 == 0;
+  dim3 grid((unsigned)tiles, ceil_div(C / vn, cv8 ? 8 : 4));
+#define STEP_POOL_GO(TT_, A, B, Cc)                                                                                   \
+  do {                                                                                                                \
+    if (cv8)                                                                                                          \
+      maxpool3d_kernel<TT_, A, B, Cc, 8><<<grid, 256, 0, cu(stream)>>>((const TT_*)x, N, T, H, W, C, in_ld, KT, KH, KW, ST, SH, \
+                                                                      SW, PT, PH, PW, pad_hi_t, pad_hi_h, pad_hi_w, OT, OH, \
+                                                                      OW, (TT_*)y, out_ld, TT, TH, TW);               \
+    else                                                                                                              \
+      maxpool3d_kernel<TT_, A, B, Cc, 4><<<grid, 256, 0, cu(stream)>>>((const TT_*)x, N, T, H, W, C, in_ld, KT, KH, KW, ST, SH, \
+                                                                      SW, PT, PH, PW, pad_hi_t, pad_hi_h, pad_hi_w, OT, OH, \
+                                                                      OW, (TT_*)y, out_ld, TT, TH, TW);               \
+  } while (0)
+  const int kind = (KT == 1 && KH == 3 && KW == 3) ? 1 : ((KT == 3 && KH == 3 && KW == 3) ? 2 : 0);
+  if (dtype == STEP_F16) {
+    if (kind == 1) STEP_POOL_GO(__half, 1, 3, 3); else if (kind == 2) STEP_POOL_GO(__half, 3, 3, 3); else STEP_POOL_GO(__half, 0, 0, 0);
+  } else {
+    if (kind == 1) STEP_POOL_GO(float, 1, 3, 3); else if (kind == 2) STEP_POOL_GO(float, 3, 3, 3); else STEP_POOL_GO(float, 0, 0, 0);
+  }
+  (void)0;
+#undef STEP_POOL_GO
   STEP_LAUNCH_CHECK("maxpool3d_kernel");
   return 0;
 }
@@ -420,7 +445,7 @@ extern "C" int step_clip_to_s2d_f16(const float* clip, int N, int T, int Cc, int
   STEP_CHECK_ARG(T % 2 == 0 && H % 2 == 0 && W % 2 == 0 && ld >= 8 * Cc, "clip_to_s2d: T,H,W must be even, ld >= 8*Cc");
   STEP_CHECK_ARG(ld % 8 == 0 && 256 % (ld / 8) == 0 && (size_t)4 * Cc * W * sizeof(float) <= 48 * 1024, "clip_to_s2d: ld must divide 2048, row tile must fit 48 KB smem");
   STEP_CHECK_ARG(((uintptr_t)out & 15) == 0, "clip_to_s2d: out must be 16-byte aligned");
-  long long rows = (long long)N * (T / 2) * (H / 2);
+  long long rows = (long long)N * (T / 2) * ceil_div(H / 2, kS2dRows);
   STEP_CHECK_ARG(rows < (1LL << 31), "clip_to_s2d: too many rows");
   clip_to_s2d_kernel<<<(unsigned)rows, 256, (size_t)4 * Cc * W * sizeof(float), cu(stream)>>>(clip, N, T, Cc, H, W, (__half*)out, ld);
   STEP_LAUNCH_CHECK("clip_to_s2d_kernel");
