@@ -172,48 +172,43 @@ __global__ void clip_to_ndhwc_kernel(const float* __restrict__ clip, int N, int 
 // clip [N,T,Cc,H,W] fp32 -> s2d [N,T/2,H/2,W/2,ld] f16, channel ((rt*2+rh)*2+rw)*Cc + c.
 // One CTA per output row (n, t2, h2): the 4*Cc input rows it needs are read coalesced into smem, then
 // each thread emits one 16-byte (8-channel) vector of one output pixel: both sides fully coalesced.
-constexpr int kS2dRows = 8;   // output rows per CTA: amortises the per-thread channel-decode setup (runtime div/mod)
+constexpr int kS2dRows = 1;   // output rows per CTA (8 was slower: fewer CTAs hide less latency)
 __global__ void __launch_bounds__(256) clip_to_s2d_kernel(const float* __restrict__ clip, int N, int T_, int Cc, int H,
                                                           int W, __half* __restrict__ out, int ld) {
   extern __shared__ float rows[];  // [rt][rh][c][W]
+  __shared__ int ch_off[64];       // output channel -> offset into rows[] (row base + rw), -1 for padding channels
   const int T2 = T_ / 2, H2 = H / 2, W2 = W / 2;
-  const int hblocks = (H2 + kS2dRows - 1) / kS2dRows;
   int r = blockIdx.x;
-  const int hb = r % hblocks; r /= hblocks;
+  const int h2 = r % H2; r /= H2;
   const int t2 = r % T2;
   const int n = r / T2;
   const int nvec = ld / 8;
-  // thread = (w2, 8-channel vector); channel ch = ((rt*2+rh)*2+rw)*Cc + c  ->  smem row (rt,rh,c), column 2*w2+rw
-  const int cvs = threadIdx.x % nvec;          // blockDim.x is a multiple of nvec (ld = 32 -> 4)
-  int srow[8], scol[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int ch = cvs * 8 + k;
-    if (ch < 8 * Cc) {
-      const int c = ch % Cc, q = ch / Cc;      // q = (rt*2+rh)*2+rw
-      srow[k] = ((q >> 1) * Cc + c) * W; scol[k] = q & 1;
-    } else { srow[k] = -1; scol[k] = 0; }
+  // channel ch = ((rt*2+rh)*2+rw)*Cc + c  ->  smem row (rt,rh,c), column 2*w2+rw.  One runtime div/mod per
+  // CHANNEL (first ld threads) instead of eight per thread: the kernel was issue-bound on that setup.
+  if (threadIdx.x < ld && threadIdx.x < 64) {
+    const int ch = threadIdx.x;
+    int off = -1;
+    if (ch < 8 * Cc) { const int c = ch % Cc, q = ch / Cc; off = ((q >> 1) * Cc + c) * W + (q & 1); }
+    ch_off[ch] = off;
   }
-  for (int hh = 0; hh < kS2dRows; ++hh) {
-    const int h2 = hb * kS2dRows + hh;
-    if (h2 >= H2) break;
-    // 4*Cc input rows, each W contiguous floats
-    for (int rt = 0; rt < 2; ++rt)
-      for (int rh = 0; rh < 2; ++rh)
-        for (int c = 0; c < Cc; ++c) {
-          const float* src = clip + ((((size_t)n * T_ + 2 * t2 + rt) * Cc + c) * H + 2 * h2 + rh) * W;
-          float* dst = rows + ((rt * 2 + rh) * Cc + c) * W;
-          for (int w = threadIdx.x; w < W; w += blockDim.x) dst[w] = src[w];
-        }
-    __syncthreads();
-    __half* orow = out + (((size_t)n * T2 + t2) * H2 + h2) * W2 * ld;
-    for (int w2 = threadIdx.x / nvec; w2 < W2; w2 += blockDim.x / nvec) {
-      float v[8];
+  for (int rt = 0; rt < 2; ++rt)
+    for (int rh = 0; rh < 2; ++rh)
+      for (int c = 0; c < Cc; ++c) {
+        const float* src = clip + ((((size_t)n * T_ + 2 * t2 + rt) * Cc + c) * H + 2 * h2 + rh) * W;
+        float* dst = rows + ((rt * 2 + rh) * Cc + c) * W;
+        for (int w = threadIdx.x; w < W; w += blockDim.x) dst[w] = src[w];
+      }
+  __syncthreads();
+  const int cvs = threadIdx.x % nvec;          // blockDim.x is a multiple of nvec (ld = 32 -> 4)
+  int offs[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = srow[k] >= 0 ? rows[srow[k] + 2 * w2 + scol[k]] : 0.0f;
-      store16(orow + (size_t)w2 * ld + cvs * 8, v);
-    }
-    __syncthreads();
+  for (int k = 0; k < 8; ++k) offs[k] = ch_off[cvs * 8 + k];
+  __half* orow = out + (((size_t)n * T2 + t2) * H2 + h2) * W2 * ld;
+  for (int w2 = threadIdx.x / nvec; w2 < W2; w2 += blockDim.x / nvec) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = offs[k] >= 0 ? rows[offs[k] + 2 * w2] : 0.0f;
+    store16(orow + (size_t)w2 * ld + cvs * 8, v);
   }
 }
 
@@ -443,7 +438,7 @@ extern "C" int step_clip_to_s2d_f16(const float* clip, int N, int T, int Cc, int
                                     step_stream_t stream) {
   STEP_CHECK_ARG(clip && out && N > 0 && T > 0 && Cc > 0 && H > 0 && W > 0, "clip_to_s2d: bad args");
   STEP_CHECK_ARG(T % 2 == 0 && H % 2 == 0 && W % 2 == 0 && ld >= 8 * Cc, "clip_to_s2d: T,H,W must be even, ld >= 8*Cc");
-  STEP_CHECK_ARG(ld % 8 == 0 && 256 % (ld / 8) == 0 && (size_t)4 * Cc * W * sizeof(float) <= 48 * 1024, "clip_to_s2d: ld must divide 2048, row tile must fit 48 KB smem");
+  STEP_CHECK_ARG(ld % 8 == 0 && ld <= 64 && 256 % (ld / 8) == 0 && (size_t)4 * Cc * W * sizeof(float) <= 48 * 1024, "clip_to_s2d: ld must divide 2048, row tile must fit 48 KB smem");
   STEP_CHECK_ARG(((uintptr_t)out & 15) == 0, "clip_to_s2d: out must be 16-byte aligned");
   long long rows = (long long)N * (T / 2) * ceil_div(H / 2, kS2dRows);
   STEP_CHECK_ARG(rows < (1LL << 31), "clip_to_s2d: too many rows");
