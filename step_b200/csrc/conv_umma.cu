@@ -45,6 +45,8 @@ struct ConvGeom {
   int n_stages_p, mh, tmem_bufs;  // persistent kernel: pipeline depth, 128-row halves per tile, accumulator sets
   int res_tma;                    // residual tile fetched by TMA into shared memory (LINEAR mode, BN % 64 == 0)
   int cluster;                    // 1, or 2: CTA pairs sharing the weight tile by TMA multicast
+  int tma_store;                  // epilogue writes 32-row x 16-column slabs with bulk tensor stores (linear M)
+  int col_split;                  // mh == 1: columns [0, col_split) -> epilogue warps 2..5, the rest -> warps 6..9
   int n_splits, split[2], ld_extra[2], coff_extra[2];  // fused 1x1x1 layers: extra destinations by column range
   __half* y_extra[2];
   int Cout, out_ld, out_coff, res_ld, res_coff, relu;
@@ -125,6 +127,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// bulk tensor store shared -> global (2-D map, coordinates {column, row}); out-of-range elements are not written
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -357,6 +374,7 @@ constexpr int kThreadsP = 64 + kEpiWarps * 32;     // warp 0 producer, warp 1 MM
 constexpr int kMaxBNP = 256;
 constexpr int kSlabChunk = 32;                     // columns staged per pass by an epilogue warp
 constexpr int kSlabPitch = kSlabChunk * 2 + 16;    // 80 B: odd multiple of 16 -> conflict-free 16-byte stores
+constexpr int kSlabBytes = 4096;                   // per epilogue warp: 2 buffers x 2 halves x (32 rows x 32 B, 32B-swizzled)
 constexpr int kBookBytesP = 4096 + 4 * 2 * kMaxBNP * 4;           // barriers (first 4 KB) + [tile & 3][scale|shift][BN]
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -403,8 +421,9 @@ __device__ __forceinline__ HalfOrigin half_origin(const ConvGeom& g, int m_tile)
 template <int BK, bool kHasRes>
 __global__ void __launch_bounds__(kThreadsP, 1)
 conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_bh, ConvGeom g,
-                         int total_tiles,
+                         const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_bh,
+                         const __grid_constant__ CUtensorMap map_y0, const __grid_constant__ CUtensorMap map_y1,
+                         const __grid_constant__ CUtensorMap map_y2, ConvGeom g, int total_tiles,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const __half* __restrict__ residual, __half* __restrict__ y) {
   constexpr int kABytes = kBM * BK * 2;
@@ -423,7 +442,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   const int stage_bytes = mh * kABytes + b_bytes;  // multiple of 1024 (BN % 16 == 0)
   uint8_t* slabs = smem + (size_t)g.n_stages_p * stage_bytes;   // [kEpiWarps][32 rows][kSlabPitch]
   // residual tiles (kHasRes && g.res_tma): [2 buffers][BN/64 boxes][128 rows x 128 B, 128B-swizzled], 1024-aligned
-  uint8_t* rbuf = (uint8_t*)(((uintptr_t)(slabs + (size_t)kEpiWarps * 32 * kSlabPitch) + 1023) & ~(uintptr_t)1023);
+  uint8_t* rbuf = (uint8_t*)(((uintptr_t)(slabs + (size_t)kEpiWarps * kSlabBytes) + 1023) & ~(uintptr_t)1023);
   const bool res_tma = kHasRes && g.res_tma;
   const int res_boxes = g.BN >> 6;
 
@@ -562,11 +581,10 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     const int lane_grp = warp & 3;                 // TMEM lane quarter this warp may access
     const int sel = ew >> 2;                       // 0 / 1
     const int hsel = mh == 2 ? sel : 0;            // which 128-row half
-    const int chunks16 = g.BN >> 4;
-    const int col0 = (mh == 2 || sel == 0) ? 0 : ((chunks16 + 1) / 2) * 16;
-    const int col1 = (mh == 2 || sel == 1) ? g.BN : ((chunks16 + 1) / 2) * 16;
+    const int col0 = (mh == 2 || sel == 0) ? 0 : g.col_split;
+    const int col1 = (mh == 2 || sel == 1) ? g.BN : g.col_split;
     const int ncol = col1 - col0;                  // multiple of 16, may be 0
-    uint8_t* slab = slabs + (size_t)ew * 32 * kSlabPitch;
+    uint8_t* slab = slabs + (size_t)ew * kSlabBytes;
     uint8_t* srow = slab + (size_t)lane * kSlabPitch;
     const int row = lane_grp * 32 + lane;
     auto row_pixel = [&](int m_tile) -> long long {
@@ -582,6 +600,8 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       long long m = o.m0 + row;
       return m < g.M ? m : -1;
     };
+    const bool tma_st = g.tma_store != 0;
+    int pass = 0;                                  // bulk-store passes issued by this warp (slab double buffer)
     int it = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
       const int buf = nbuf == 2 ? (it & 1) : 0;
@@ -607,6 +627,81 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       const __half* rrow = (kHasRes && pix >= 0) ? residual + (size_t)pix * g.res_ld + g.res_coff + nbase : nullptr;
       const uint8_t* rtile = rbuf + (size_t)(it & 1) * res_boxes * (kBM * 128);
       if (res_tma) mbar_wait(&rfull_bar[it & 1], ((uint32_t)it >> 1) & 1u);
+      if (tma_st) {
+        // 32-column passes: TMEM -> registers -> scale/shift/residual/ReLU -> fp16 slab -> bulk tensor stores.  The slab
+        // is two 16-column halves ([32 rows][32 B], 32B-swizzled); a half never straddles a destination boundary (splits
+        // are multiples of 16), and the store engine clips rows >= M and columns past the destination's width.
+        const int row0 = (mt * mh + hsel) * kBM + lane_grp * 32;
+        for (int cb = 0; cb < ncol; cb += 32, ++pass) {
+          const int cw = min(32, ncol - cb);       // 32, or 16 in the tail of an odd tile
+          const bool last = cb + 32 >= ncol;
+          uint8_t* sl = slab + (size_t)(pass & 1) * 2048;
+          uint4 rreg[4];
+          if (kHasRes) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              rreg[j] = make_uint4(0, 0, 0, 0);
+              if (j * 8 < cw) {
+                if (res_tma) {
+                  const int tc = col0 + cb + j * 8;
+                  rreg[j] = *reinterpret_cast<const uint4*>(rtile + (size_t)(tc >> 6) * (kBM * 128) + row * 128 +
+                                                            ((((tc & 63) >> 3) ^ (row & 7)) << 4));
+                } else if (rrow && nbase + cb + j * 8 < g.Cout) {
+                  rreg[j] = *reinterpret_cast<const uint4*>(rrow + cb + j * 8);
+                }
+              }
+            }
+          }
+          uint32_t v[32];
+          if (cw == 32) tmem_ld32(taddr + cb, v); else tmem_ld16(taddr + cb, v);
+          // the bulk stores that read this slab buffer two passes ago must have drained it
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q * 8 < cw) {
+              const float4 a0 = *reinterpret_cast<const float4*>(s_scale + cb + q * 8);
+              const float4 a1 = *reinterpret_cast<const float4*>(s_scale + cb + q * 8 + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(s_shift + cb + q * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_shift + cb + q * 8 + 4);
+              float f[8];
+              f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), a0.x, b0.x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), a0.y, b0.y);
+              f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), a0.z, b0.z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), a0.w, b0.w);
+              f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), a1.x, b1.x); f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), a1.y, b1.y);
+              f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), a1.z, b1.z); f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), a1.w, b1.w);
+              if (kHasRes) {
+                const __half2* hp = reinterpret_cast<const __half2*>(&rreg[q]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float2 rf = __half22float2(hp[k]);
+                  f[2 * k] += rf.x; f[2 * k + 1] += rf.y;
+                }
+              }
+              if (g.relu) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+              }
+              store16(reinterpret_cast<__half*>(sl + (q >> 1) * 1024 + lane * 32 + (((q & 1) ^ ((lane >> 2) & 1)) << 4)), f);
+            }
+          }
+          if (last) tc_fence_before();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (last) mbar_arrive(&tempty_bar[buf]);   // accumulator fully read by this warp
+            for (int h = 0; h * 16 < cw; ++h) {
+              const int gc = nbase + cb + h * 16;
+              if (gc >= g.Cout) break;
+              int d = 0, ds = 0;
+              if (g.n_splits > 0 && gc >= g.split[0]) { d = 1; ds = g.split[0]; }
+              if (g.n_splits > 1 && gc >= g.split[1]) { d = 2; ds = g.split[1]; }
+              tma_store_2d(d == 0 ? &map_y0 : (d == 1 ? &map_y1 : &map_y2), sl + h * 1024, gc - ds, row0);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else
       for (int cb = 0; cb < ncol; cb += kSlabChunk) {
         const int cw = min(kSlabChunk, ncol - cb);   // 16 or 32 columns in this pass
         uint4 rreg[kSlabChunk / 8];
@@ -689,6 +784,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         if (lane == 0) mbar_arrive(&rempty_bar[it & 1]);
       }
     }
+    if (tma_st && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // slabs are read, writes are done
   }
   tc_fence_before();
   __syncthreads();
@@ -798,7 +894,7 @@ static int conv_variant() {
 }
 
 struct ConvPlan {
-  CUtensorMap map_a, map_b, map_r, map_bh;
+  CUtensorMap map_a, map_b, map_r, map_bh, map_y[3];
   ConvGeom g;
   int BK;
   size_t smem_bytes;
@@ -933,7 +1029,7 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
     g.tmem_bufs = (g.mh * ncols * 2 <= 512) ? 2 : 1;
     g.res_tma = (persist && p->residual && g.mh == 1 && mode == A_LINEAR && g.BN % 64 == 0 && p->Cout % 64 == 0) ? 1 : 0;
     const size_t res_bytes = g.res_tma ? (size_t)2 * (g.BN / 64) * kBM * 128 + 1024 : 0;
-    const size_t budget = 227 * 1024 - kBookBytesP - 1024 - (size_t)kEpiWarps * 32 * kSlabPitch - res_bytes;
+    const size_t budget = 227 * 1024 - kBookBytesP - 1024 - (size_t)kEpiWarps * kSlabBytes - res_bytes;
     const size_t stage_bytes = (size_t)g.mh * kBM * BK * 2 + (size_t)g.BN * BK * 2;
     int st = (int)(budget / stage_bytes);
     g.n_stages_p = st > kMaxStagesP ? kMaxStagesP : st;
@@ -948,6 +1044,33 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
       if (want && persist && g.mh == 1 && m128 >= 2 * 74 && g.BN >= 64 && (g.BN / 2) % 8 == 0) g.cluster = 2;
     }
     pl->persist_tiles = g.cluster == 2 ? (int)(((m128 + 1) / 2) * g.n_tiles) : (int)(((m128 + g.mh - 1) / g.mh) * g.n_tiles);
+    // epilogue column split between the two warp groups (mh == 1) and the store path
+    {
+      const char* e = getenv("STEP_B200_TMAST");
+      g.tma_store = (persist && mode != A_BOX && !(e && e[0] == '0')) ? 1 : 0;
+      if (g.tma_store) {
+        g.col_split = g.BN < 32 ? g.BN : (g.BN / 2 + 31) / 32 * 32;   // 32-column passes: keep the 16-wide tail to one group
+      } else {
+        g.col_split = ((g.BN / 16 + 1) / 2) * 16;
+      }
+      for (int d = 0; d < 3; ++d) pl->map_y[d] = pl->map_b;   // placeholders
+      if (g.tma_store) {
+        STEP_CHECK_ARG(g.M < (1LL << 31), "conv3d(f16): M too large");
+        for (int d = 0; d <= p->n_splits; ++d) {
+          const int ds = d ? p->split[d - 1] : 0, de = d < p->n_splits ? p->split[d] : p->Cout;
+          __half* base = d ? (__half*)p->y_extra[d - 1] + p->coff_extra[d - 1] : (__half*)p->y + p->out_coff;
+          const int ld = d ? p->ld_extra[d - 1] : p->out_ld;
+          cuuint64_t ydims[2] = {(cuuint64_t)(de - ds), (cuuint64_t)g.M};
+          cuuint64_t ystr[1] = {(cuuint64_t)ld * 2};
+          cuuint32_t ybox[2] = {16, 32};
+          const cuuint32_t ones2[2] = {1, 1};
+          CUresult cy = g_encode_tiled(&pl->map_y[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, ydims, ystr, ybox, ones2,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (cy != CUDA_SUCCESS) return fail(STEP_E_DRIVER, "conv3d(f16): tensor map (output %d) encode failed: CUresult %d", d, (int)cy);
+        }
+      }
+    }
     pl->map_bh = pl->map_b;
     if (g.cluster == 2) {
       cuuint64_t bdims[3] = {(cuuint64_t)p->Cin, (cuuint64_t)taps, (cuuint64_t)p->Cout};
@@ -959,7 +1082,7 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (cr3 != CUDA_SUCCESS) return fail(STEP_E_DRIVER, "conv3d(f16): tensor map (B half) encode failed: CUresult %d", (int)cr3);
     }
-    pl->persist_smem = kBookBytesP + 1024 + (size_t)g.n_stages_p * stage_bytes + (size_t)kEpiWarps * 32 * kSlabPitch + res_bytes;
+    pl->persist_smem = kBookBytesP + 1024 + (size_t)g.n_stages_p * stage_bytes + (size_t)kEpiWarps * kSlabBytes + res_bytes;
     if (g.res_tma) {
       cuuint64_t rdims[2] = {(cuuint64_t)p->Cout, (cuuint64_t)g.M};
       cuuint64_t rstr[1] = {(cuuint64_t)p->res_ld * 2};
@@ -1013,7 +1136,8 @@ static int launch_persist(const ConvPlan& pl, const step_conv_params* p, cudaStr
   cfg.blockDim = dim3(kThreadsP);
   cfg.dynamicSmemBytes = pl.persist_smem;
   cfg.stream = s;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_umma_persist_kernel<BK, kHasRes>, pl.map_a, pl.map_b, pl.map_r, pl.map_bh, pl.g,
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_umma_persist_kernel<BK, kHasRes>, pl.map_a, pl.map_b, pl.map_r, pl.map_bh, pl.map_y[0], pl.map_y[1],
+                                      pl.map_y[2], pl.g,
                                       total, p->scale, p->shift, (const __half*)p->residual, (__half*)p->y);
   if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "conv_umma_persist_kernel launch: %s", cudaGetErrorString(le)); }
   STEP_LAUNCH_CHECK("conv_umma_persist_kernel");

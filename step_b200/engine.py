@@ -19,6 +19,7 @@ A_MODE = {"box": L.A_BOX, "im2col": L.A_IM2COL, "auto": L.A_AUTO, "simt": L.A_SI
 # When set to a list, conv() appends (params, tensors-kept-alive) for every launch: bench.py replays
 # exactly those launches to time the dominant kernel class in isolation (roofline.achieved).
 RECORDER = None
+DEBUG_SYNC = os.environ.get("STEP_B200_DEBUG_SYNC", "0") == "1"
 
 
 # Independent branches of an Inception block (models/i3dpt.py:157-163 runs them serially) are issued on
@@ -199,6 +200,12 @@ def conv(x, w_packed, scale, shift, out, k, stride=(1, 1, 1), pad_lo=None, relu=
         p.a_mode = L.A_AUTO
     assert (out.N, out.T, out.H, out.W) == (x.N,) + tuple(out_dims), "conv: output buffer shape mismatch"
     L.check(L.lib().step_conv3d_fwd(p, L.stream()))
+    if DEBUG_SYNC:   # STEP_B200_DEBUG_SYNC=1: find the launch an asynchronous fault belongs to
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            print("conv fault:", {f: getattr(p, f) for f, _ in p._fields_ if isinstance(getattr(p, f), int)}, flush=True)
+            raise
     if RECORDER is not None:
         RECORDER.append((p, (x.buf, w_packed, scale, shift, out.buf, residual.buf if residual is not None else None,
                              [e.buf for e in (extra_outs or [])])))

@@ -256,11 +256,13 @@ def test_maxpool_tf_padding_matches_torch(case, code):
     assert torch.equal(out.buf.float().cpu(), ref)        # max is exact in either storage type
 
 
-def test_fused_1x1_multi_destination_matches_separate_convs():
-    """Mixed's three 1x1x1 branches as one GEMM whose epilogue scatters column ranges (i3dpt.py:133-147)."""
+@pytest.mark.parametrize("Cin,outs", [(832, (256, 160, 32)), (192, (64, 96, 16)), (512, (160, 112, 24)),
+                                      (512, (112, 144, 32))])
+def test_fused_1x1_multi_destination_matches_separate_convs(Cin, outs):
+    """Mixed's three 1x1x1 branches as one GEMM whose epilogue scatters column ranges (i3dpt.py:133-147);
+    mixed_3b / 4c / 4e have destination boundaries that are not multiples of 32 columns."""
     g = torch.Generator().manual_seed(11)
-    N, T, H, W, Cin = 2, 4, 7, 7, 832
-    outs = (256, 160, 32)
+    N, T, H, W = 2, 4, 7, 7
     x = torch.randn(N, T, H, W, Cin, generator=g).half().cuda()
     ws = [(torch.randn(c, Cin, 1, 1, 1, generator=g) / Cin ** 0.5).half() for c in outs]
     scale = (torch.rand(sum(outs), generator=g) + 0.5).cuda()

@@ -18,6 +18,7 @@ LAYERS = {
     "loc_1088":   (704, 1, 7, 7, 1088, 1024, (1, 1, 1), None, False),
     "loc_3x3":    (704, 1, 7, 7, 256, 256, (1, 3, 3), None, False),
     "loc_res":    (704, 1, 7, 7, 256, 1024, (1, 1, 1), None, True),
+    "loc_nores":  (704, 1, 7, 7, 256, 1024, (1, 1, 1), None, False),
     "loc_1024":   (704, 1, 7, 7, 1024, 256, (1, 1, 1), None, False),
     "5b_fused":   (88, 8, 7, 7, 832, 448, (1, 1, 1), None, False),
     "4b_fused":   (8, 8, 14, 14, 480, 304, (1, 1, 1), None, False),
