@@ -4,6 +4,8 @@
 // MaxPool3dTFPadding (models/i3dpt.py:114-126) = ConstantPad3d(0) + MaxPool3d(ceil_mode=True):
 // the padded cells hold 0 (not -inf), and windows may hang over the *padded* extent (ceil mode),
 // where they see nothing.  Everything is 16-byte vectorised along C.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace step {
@@ -141,6 +143,70 @@ __global__ void __launch_bounds__(256, 3) maxpool3d_333_kernel(const T* __restri
   }
 }
 
+
+// Same pooling, separable and marching along t: a thread owns a 7-pixel row segment x one 16-byte channel vector and
+// walks TS output planes.  For every input plane it loads the 3 x 9 neighbourhood once, reduces it over (h, w) into a
+// 7-vector P[tt], and emits out[t] = max(P[t-1], P[t], P[t+1]) from two carried 7-vectors: 27 loads and 70 vector
+// maxima per plane instead of 81 and 182 per output row.  The kernel is latency bound on the small maps, so the host
+// picks TS to keep ~50k threads in flight.
+template <typename T>
+__global__ void __launch_bounds__(128) maxpool3d_333_march_kernel(const T* __restrict__ x, int N, int T_, int H, int W, int C,
+                                                                  int in_ld, T* __restrict__ y, int out_ld, int TS) {
+  constexpr int VN = Vec16<T>::N, WB = 7;
+  const int nvec = C / VN, wsegs = W / WB, tsegs = (T_ + TS - 1) / TS;
+  const long long total = (long long)N * tsegs * H * wsegs * nvec;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % nvec);
+  long long r = idx / nvec;
+  const int ws = (int)(r % wsegs); r /= wsegs;
+  const int h = (int)(r % H); r /= H;
+  const int ts = (int)(r % tsegs);
+  const int n = (int)(r / tsegs);
+  const int w0 = ws * WB, t0 = ts * TS, t1 = min(T_, t0 + TS);
+  const bool wl = w0 > 0, wr = w0 + WB < W;
+  const uint4 lo = vec_lowest<T>();
+  uint4 p1[WB], m2[WB];
+#pragma unroll
+  for (int j = 0; j < WB; ++j) { p1[j] = lo; m2[j] = lo; }
+  for (int tt = t0 - 1; tt <= t1; ++tt) {
+    uint4 pc[WB];
+#pragma unroll
+    for (int j = 0; j < WB; ++j) pc[j] = lo;
+    if (tt >= 0 && tt < T_) {
+      uint4 v[3][WB + 2];
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh) {
+        const int hh = h + dh - 1;
+        const bool hv = hh >= 0 && hh < H;
+        const T* rowp = x + ((((size_t)n * T_ + tt) * H + (hv ? hh : h)) * W + w0) * in_ld + cv * VN;
+        v[dh][0] = (hv && wl) ? *reinterpret_cast<const uint4*>(rowp - in_ld) : lo;
+#pragma unroll
+        for (int j = 0; j < WB; ++j) v[dh][j + 1] = hv ? *reinterpret_cast<const uint4*>(rowp + (size_t)j * in_ld) : lo;
+        v[dh][WB + 1] = (hv && wr) ? *reinterpret_cast<const uint4*>(rowp + (size_t)WB * in_ld) : lo;
+      }
+#pragma unroll
+      for (int j = 0; j < WB + 2; ++j) v[0][j] = vec_max<T>(v[0][j], vec_max<T>(v[1][j], v[2][j]));
+#pragma unroll
+      for (int j = 0; j < WB; ++j) pc[j] = vec_max<T>(v[0][j], vec_max<T>(v[0][j + 1], v[0][j + 2]));
+    }
+    const int t = tt - 1;
+    if (t >= t0) {
+      // windows that overlap the zero padding see a 0 (ConstantPad3d, i3dpt.py:120)
+      const bool edge_th = (t == 0) || (t == T_ - 1) || (h == 0) || (h == H - 1);
+      T* orow = y + ((((size_t)n * T_ + t) * H + h) * W + w0) * out_ld + cv * VN;
+#pragma unroll
+      for (int j = 0; j < WB; ++j) {
+        uint4 m = vec_max<T>(m2[j], pc[j]);
+        if (edge_th || (w0 + j == 0) || (w0 + j == W - 1)) m = vec_max<T>(m, make_uint4(0, 0, 0, 0));
+        *reinterpret_cast<uint4*>(orow + (size_t)j * out_ld) = m;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < WB; ++j) { m2[j] = vec_max<T>(p1[j], pc[j]); p1[j] = pc[j]; }
+  }
+}
+
 // x [A,B,P,C] (C contiguous, pixel stride ld) -> y [A, P*C]  (mean over B, fp32 accumulate in index order)
 template <typename TI, typename TO>
 __global__ void mean_mid_kernel(const TI* __restrict__ x, int A, int B, int P, int C, int ld, TO* __restrict__ y) {
@@ -152,6 +218,29 @@ __global__ void mean_mid_kernel(const TI* __restrict__ x, int A, int B, int P, i
   float s = 0.0f;
   for (int b = 0; b < B; ++b) s += to_f32<TI>(x[(((size_t)a * B + b) * P + p) * ld + c]);
   y[idx] = from_f32<TO>(s / (float)B);
+}
+
+// fp16 input, 8 channels per thread (16-byte loads); the per-channel sums run in the same index order as above
+template <typename TO>
+__global__ void mean_mid_h8_kernel(const __half* __restrict__ x, int A, int B, int P, int C, int ld, TO* __restrict__ y) {
+  const int cv = C >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)A * P * cv) return;
+  const int c = (int)(idx % cv) * 8;
+  const int p = (int)((idx / cv) % P);
+  const int a = (int)(idx / ((long long)cv * P));
+  float s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.0f;
+  for (int b = 0; b < B; ++b) {
+    float v[8];
+    load16(x + (((size_t)a * B + b) * P + p) * ld + c, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += v[k];
+  }
+  TO* o = y + ((size_t)a * P + p) * C + c;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = from_f32<TO>(s[k] / (float)B);
 }
 
 // clip [N,T,Cc,H,W] fp32 -> [N,T,H,W,ld]
@@ -305,6 +394,76 @@ __global__ void __launch_bounds__(256) linear_splitk_kernel(const T* __restrict_
   }
 }
 
+
+// fp16 operands: the same split-K tiling on mma.sync tensor-core tiles, no shared memory.  One warp owns 16 rows and
+// all N (<= 64) columns; per 32-column block every thread loads ONE 16-byte vector from each of its two rows of x and
+// from one weight row per 8-column tile and feeds the four k-pairs it holds to two m16n8k16 steps.  The k order inside
+// a block is therefore permuted (thread t covers columns 8t..8t+7), identically for x and w, which a dot product does
+// not care about; x is streamed exactly once with full 32-byte sectors.
+__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(128) linear_mma_kernel(const __half* __restrict__ x, int M, int K, int x_ld,
+                                                         const __half* __restrict__ w, int N,
+                                                         const int32_t* __restrict__ row_map, float* __restrict__ partial) {
+  const int kc = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.y * 64 + warp * 16;
+  if (m0 >= M) return;
+  const int k0 = kc * kLinKC, klen = min(kLinKC, K - k0);   // multiple of 8
+  const int r0 = m0 + g, r1 = m0 + g + 8;
+  const bool v0 = r0 < M, v1 = r1 < M;
+  const __half* xa = x + (size_t)(v0 ? (row_map ? row_map[r0] : r0) : 0) * x_ld + k0 + t * 8;
+  const __half* xb = x + (size_t)(v1 ? (row_map ? row_map[r1] : r1) : 0) * x_ld + k0 + t * 8;
+  const __half* wp[NT];
+  bool wv[NT];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    wv[j] = j * 8 + g < N;
+    wp[j] = w + (size_t)(wv[j] ? j * 8 + g : 0) * K + k0 + t * 8;
+  }
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll 4
+  for (int kb = 0; kb < klen; kb += 32) {
+    const bool in = kb + t * 8 < klen;
+    const uint4 a = (in && v0) ? *reinterpret_cast<const uint4*>(xa + kb) : zero;
+    const uint4 b = (in && v1) ? *reinterpret_cast<const uint4*>(xb + kb) : zero;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint4 q = (in && wv[j]) ? *reinterpret_cast<const uint4*>(wp[j] + kb) : zero;
+      mma_16816(acc[j], a.x, b.x, a.y, b.y, q.x, q.y);
+      mma_16816(acc[j], a.z, b.z, a.w, b.w, q.z, q.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int n = j * 8 + 2 * t;
+    if (v0) {
+      if (n < N) partial[((size_t)kc * M + r0) * N + n] = acc[j][0];
+      if (n + 1 < N) partial[((size_t)kc * M + r0) * N + n + 1] = acc[j][1];
+    }
+    if (v1) {
+      if (n < N) partial[((size_t)kc * M + r1) * N + n] = acc[j][2];
+      if (n + 1 < N) partial[((size_t)kc * M + r1) * N + n + 1] = acc[j][3];
+    }
+  }
+}
+
+static void launch_linear_mma(const __half* x, int M, int K, int x_ld, const __half* w, int N, const int32_t* row_map,
+                              float* partial, cudaStream_t s) {
+  dim3 grid(ceil_div(K, kLinKC), ceil_div(M, 64));
+  if (N <= 8) linear_mma_kernel<1><<<grid, 128, 0, s>>>(x, M, K, x_ld, w, N, row_map, partial);
+  else if (N <= 16) linear_mma_kernel<2><<<grid, 128, 0, s>>>(x, M, K, x_ld, w, N, row_map, partial);
+  else if (N <= 32) linear_mma_kernel<4><<<grid, 128, 0, s>>>(x, M, K, x_ld, w, N, row_map, partial);
+  else linear_mma_kernel<8><<<grid, 128, 0, s>>>(x, M, K, x_ld, w, N, row_map, partial);
+}
+
 __global__ void linear_reduce_kernel(const float* __restrict__ partial, int ksplit, int M, int N,
                                      const float* __restrict__ bias, float* __restrict__ y, int y_ld, int act,
                                      int accumulate) {
@@ -364,14 +523,31 @@ extern "C" int step_maxpool3d_fwd(const void* x, int dtype, int N, int T, int H,
   STEP_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "maxpool3d: pointers must be 16-byte aligned");
   if (KT == 3 && KH == 3 && KW == 3 && ST == 1 && SH == 1 && SW == 1 && PT == 1 && PH == 1 && PW == 1 && pad_hi_t == 1 &&
       pad_hi_h == 1 && pad_hi_w == 1 && OT == T && OH == H && OW == W && W % 7 == 0) {
-    long long total = (long long)N * T * H * (W / 7) * (C / vn);
+    const char* pv = getenv("STEP_B200_POOL333");
+    if (pv && pv[0] == '0') {   // previous kernel, kept for A/B timing
+      long long total = (long long)N * T * H * (W / 7) * (C / vn);
+      if (dtype == STEP_F16)
+        maxpool3d_333_kernel<__half><<<grid_for(total, 256), 256, 0, cu(stream)>>>((const __half*)x, N, T, H, W, C, in_ld,
+                                                                                   (__half*)y, out_ld);
+      else
+        maxpool3d_333_kernel<float><<<grid_for(total, 256), 256, 0, cu(stream)>>>((const float*)x, N, T, H, W, C, in_ld,
+                                                                                  (float*)y, out_ld);
+      STEP_LAUNCH_CHECK("maxpool3d_333_kernel");
+      return 0;
+    }
+    const long long per_seg = (long long)N * H * (W / 7) * (C / vn);
+    int TS = T;
+    while (TS > 2 && per_seg * ceil_div(T, TS) < 50000) TS = (TS + 1) / 2;
+    if (pv && atoi(pv) >= 2) TS = atoi(pv) < T ? atoi(pv) : T;
+    const long long total = per_seg * ceil_div(T, TS);
+    STEP_CHECK_ARG(ceil_div(total, 128) < (1LL << 31), "maxpool3d: too many blocks");
     if (dtype == STEP_F16)
-      maxpool3d_333_kernel<__half><<<grid_for(total, 256), 256, 0, cu(stream)>>>((const __half*)x, N, T, H, W, C, in_ld,
-                                                                                 (__half*)y, out_ld);
+      maxpool3d_333_march_kernel<__half><<<(unsigned)ceil_div(total, 128), 128, 0, cu(stream)>>>((const __half*)x, N, T, H, W, C,
+                                                                                                 in_ld, (__half*)y, out_ld, TS);
     else
-      maxpool3d_333_kernel<float><<<grid_for(total, 256), 256, 0, cu(stream)>>>((const float*)x, N, T, H, W, C, in_ld,
-                                                                                (float*)y, out_ld);
-    STEP_LAUNCH_CHECK("maxpool3d_333_kernel");
+      maxpool3d_333_march_kernel<float><<<(unsigned)ceil_div(total, 128), 128, 0, cu(stream)>>>((const float*)x, N, T, H, W, C,
+                                                                                                in_ld, (float*)y, out_ld, TS);
+    STEP_LAUNCH_CHECK("maxpool3d_333_march_kernel");
     return 0;
   }
   // tile: up to 4 x 8 x 8 output pixels (whole rows on the small maps), 64-byte channel chunks
@@ -408,6 +584,14 @@ extern "C" int step_mean_mid(const void* x, int dtype, int A, int B, int P, int 
   STEP_CHECK_ARG(x && y && A > 0 && B > 0 && P > 0 && C > 0 && ld >= C, "mean_mid: bad args");
   long long total = (long long)A * P * C;
   int g = ceil_div(total, 256);
+  if (dtype == STEP_F16 && C % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0) {
+    const int g8 = ceil_div(total / 8, 256);
+    if (out_dtype == STEP_F16) mean_mid_h8_kernel<__half><<<g8, 256, 0, cu(stream)>>>((const __half*)x, A, B, P, C, ld, (__half*)y);
+    else if (out_dtype == STEP_F32) mean_mid_h8_kernel<float><<<g8, 256, 0, cu(stream)>>>((const __half*)x, A, B, P, C, ld, (float*)y);
+    else return fail(STEP_E_UNSUPPORTED, "mean_mid: dtype combination %d -> %d", dtype, out_dtype);
+    STEP_LAUNCH_CHECK("mean_mid_h8_kernel");
+    return 0;
+  }
   if (dtype == STEP_F16 && out_dtype == STEP_F16)
     mean_mid_kernel<__half, __half><<<g, 256, 0, cu(stream)>>>((const __half*)x, A, B, P, C, ld, (__half*)y);
   else if (dtype == STEP_F16 && out_dtype == STEP_F32)
@@ -496,8 +680,7 @@ extern "C" int step_linear_small_n(const void* x, int dtype, int M, int K, int x
   STEP_CHECK_ARG(grid.y <= 65535, "linear_small_n: M too large");
   const int threads = N >= 8 ? 256 : 32 * N;
   if (dtype == STEP_F16)
-    linear_splitk_kernel<__half><<<grid, threads, 0, cu(stream)>>>((const __half*)x, M, K, x_ld, (const __half*)w, N,
-                                                                    row_map, (float*)workspace);
+    launch_linear_mma((const __half*)x, M, K, x_ld, (const __half*)w, N, row_map, (float*)workspace, cu(stream));
   else
     linear_splitk_kernel<float><<<grid, threads, 0, cu(stream)>>>((const float*)x, M, K, x_ld, (const float*)w, N,
                                                                    row_map, (float*)workspace);
@@ -524,8 +707,7 @@ extern "C" int step_head_regress(const void* x, int dtype, int R, int T, int K, 
   dim3 grid(ksplit, ceil_div(M, kLinRows));
   STEP_CHECK_ARG(grid.y <= 65535, "head_regress: too many rows");
   if (dtype == STEP_F16)
-    linear_splitk_kernel<__half><<<grid, 256, 0, cu(stream)>>>((const __half*)x, M, K, x_ld, (const __half*)w12, 12, nullptr,
-                                                               (float*)workspace);
+    launch_linear_mma((const __half*)x, M, K, x_ld, (const __half*)w12, 12, nullptr, (float*)workspace, cu(stream));
   else
     linear_splitk_kernel<float><<<grid, 256, 0, cu(stream)>>>((const float*)x, M, K, x_ld, (const float*)w12, 12, nullptr,
                                                               (float*)workspace);

@@ -232,6 +232,8 @@ POOL_CASES = [
     # N, T, H, W, C, k, s
     (2, 4, 7, 7, 64, (3, 3, 3), (1, 1, 1)),      # specialised 3x3x3 kernel (W % 7 == 0)
     (1, 3, 14, 28, 32, (3, 3, 3), (1, 1, 1)),
+    (1, 7, 7, 14, 16, (3, 3, 3), (1, 1, 1)),     # t segments of 2 with a 1-plane tail
+    (1, 1, 7, 7, 8, (3, 3, 3), (1, 1, 1)),       # a single plane
     (1, 4, 9, 10, 16, (3, 3, 3), (1, 1, 1)),     # generic kernel
     (1, 4, 12, 14, 24, (1, 3, 3), (1, 2, 2)),
     (2, 5, 13, 25, 8, (3, 3, 3), (2, 2, 2)),     # odd sizes: ceil_mode overhang + TF padding
@@ -301,3 +303,37 @@ def test_cluster_multicast_variant_matches(monkeypatch):
         outs[mode] = (run_conv(x, w, L.F16, (1, 1, 1), (1, 1, 1), scale, shift, True, None, L.A_AUTO).float(),
                       run_conv(x, w, L.F16, (1, 1, 1), (1, 1, 1), scale, shift, True, res, L.A_AUTO).float())
     assert torch.equal(outs["1"][0], outs["2"][0]) and torch.equal(outs["1"][1], outs["2"][1])
+
+
+# ---- small-N linear layers / temporal mean of the head (two_branch.py:246-270) -------------------------------------
+@pytest.mark.parametrize("code", [L.F32, L.F16], ids=["fp32", "fp16"])
+@pytest.mark.parametrize("M,K,N", [(100, 12544, 12), (37, 1000, 4), (88, 1024, 60), (5, 520, 33)])
+def test_linear_small_n_matches_torch(M, K, N, code):
+    g = torch.Generator().manual_seed(3)
+    dt = E.torch_dtype(code)
+    x = torch.randn(M + 3, K, generator=g).to(dt).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dt).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    rows = torch.randperm(M + 3, generator=g)[:M].to(torch.int32).cuda()
+    y = E.linear_small_n(x, M, K, K, w, b, N, row_map=rows)
+    ref = x.float()[rows.long()] @ w.float().t() + b
+    tol = 1e-4 if code == L.F32 else 1e-3
+    assert float((y - ref).abs().max()) <= tol * float(ref.abs().max()) + tol
+    # accumulate + sigmoid on top of an existing y, no bias, identity rows
+    y2 = E.linear_small_n(x, M, K, K, w, None, N, y=y.clone(), act=1, accumulate=True)
+    ref2 = torch.sigmoid(y + x.float()[:M] @ w.float().t())
+    assert float((y2 - ref2).abs().max()) <= 2e-3
+    # bit-for-bit repeatable (fixed reduction order over the K split)
+    assert torch.equal(E.linear_small_n(x, M, K, K, w, b, N, row_map=rows), y)
+
+
+@pytest.mark.parametrize("out_code", [L.F32, L.F16], ids=["to_fp32", "to_fp16"])
+def test_mean_mid_fp16_matches_torch(out_code):
+    g = torch.Generator().manual_seed(4)
+    A, B, P, C, ld = 5, 8, 49, 256, 1088
+    buf = torch.randn(A, B, P, ld, generator=g).half().cuda()
+    view = buf[..., 832:832 + C]
+    y = E.mean_mid(view.data_ptr(), L.F16, A, B, P, C, ld, buf.device, out_code)
+    ref = view.float().mean(1).reshape(A, P * C)
+    tol = 1e-6 if out_code == L.F32 else 2e-3
+    assert float((y.float() - ref).abs().max()) <= tol * float(ref.abs().max()) + tol
