@@ -20,6 +20,7 @@ A_MODE = {"box": L.A_BOX, "im2col": L.A_IM2COL, "auto": L.A_AUTO, "simt": L.A_SI
 # exactly those launches to time the dominant kernel class in isolation (roofline.achieved).
 RECORDER = None
 DEBUG_SYNC = os.environ.get("STEP_B200_DEBUG_SYNC", "0") == "1"
+STEM_HALO = os.environ.get("STEP_B200_STEM_HALO", "1") != "0"
 
 
 # Independent branches of an Inception block (models/i3dpt.py:157-163 runs them serially) are issued on

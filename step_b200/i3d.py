@@ -71,8 +71,9 @@ class Unit3Dpy(torch.nn.Module):
         """fp16 stem: x_s2d is the space-to-depth clip [N, T/2, H/2, W/2, 32]; 4x4x4 filter, pad 1."""
         w, scale, shift = self.packed(L.F16, s2d=True)
         out = Act.empty(x_s2d.N, x_s2d.T, x_s2d.H, x_s2d.W, self.conv3d.out_channels, L.F16, x_s2d.device)
+        # patch-in-shared-memory kernel (csrc/conv_halo.cu) unless STEP_B200_STEM_HALO=0
         return E.conv(x_s2d, w, scale, shift, out, (4, 4, 4), (1, 1, 1), (1, 1, 1), self.activation is not None,
-                      out_dims=(x_s2d.T, x_s2d.H, x_s2d.W))
+                      a_mode=L.A_HALO if E.STEM_HALO else None, out_dims=(x_s2d.T, x_s2d.H, x_s2d.W))
 
 
 class MaxPool3dTFPadding(torch.nn.Module):

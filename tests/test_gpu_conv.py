@@ -337,3 +337,35 @@ def test_mean_mid_fp16_matches_torch(out_code):
     ref = view.float().mean(1).reshape(A, P * C)
     tol = 1e-6 if out_code == L.F32 else 2e-3
     assert float((y.float() - ref).abs().max()) <= tol * float(ref.abs().max()) + tol
+
+
+# ---- patch-in-shared-memory kernel (csrc/conv_halo.cu) against the TMA-im2col kernel ---------------------------------
+HALO_CASES = [
+    # N, T, H, W, Cin, Cout, k, pad_lo
+    (2, 4, 32, 24, 32, 64, (4, 4, 4), (1, 1, 1)),     # the s2d stem shape (even tiles)
+    (1, 3, 20, 13, 32, 64, (4, 4, 4), (1, 1, 1)),     # ragged in t, h and w
+    (1, 5, 17, 9, 16, 32, (3, 3, 3), None),           # 32-byte rows
+    (1, 4, 14, 14, 64, 128, (3, 3, 3), None),         # 128-byte rows, one accumulator set per CTA
+    (2, 1, 7, 7, 32, 40, (1, 3, 3), None),            # 2-D filter, Cout not a multiple of 32
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_halo_kernel_matches_im2col_kernel(case):
+    N, T, H, W, Cin, Cout, k, pad = case
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(N, T, H, W, Cin, generator=g).half().cuda()
+    w = (torch.randn(Cout, Cin, *k, generator=g) / (Cin * k[0] * k[1] * k[2]) ** 0.5).half()
+    scale = (torch.rand(Cout, generator=g) + 0.5).cuda()
+    shift = torch.randn(Cout, generator=g).cuda()
+    wp = E.pack_conv_weight(w.cuda(), L.F16)
+    outs = []
+    for mode in (L.A_HALO, L.A_IM2COL):
+        buf = torch.zeros((N, T, H, W, Cout + 16), dtype=torch.float16, device="cuda")
+        E.conv(Act(x), wp, scale, shift, Act(buf, Cout, 8), k, (1, 1, 1), pad, True, None, a_mode=mode, out_dims=(T, H, W))
+        torch.cuda.synchronize()
+        outs.append(buf)
+    assert float(outs[0][..., :8].abs().max()) == 0 and float(outs[0][..., 8 + Cout:].abs().max()) == 0
+    # same products, same fp32 accumulator, different summation order inside the tensor core at most
+    err = float((outs[0].float() - outs[1].float()).abs().max())
+    assert err <= 2e-3 * float(outs[1].float().abs().max()) + 1e-3, err

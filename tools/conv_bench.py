@@ -10,6 +10,11 @@ LAYERS = {
     # name: (N, T, H, W, Cin, Cout, k, pad, residual)
     "stem_s2d":   (8, 16, 112, 112, 32, 64, (4, 4, 4), (1, 1, 1), False),
     "conv2c":     (8, 16, 56, 56, 64, 192, (3, 3, 3), None, False),
+    "3b_b2b":     (8, 16, 28, 28, 16, 32, (3, 3, 3), None, False),
+    "3c_b2b":     (8, 16, 28, 28, 32, 96, (3, 3, 3), None, False),
+    "4e_b2b":     (8, 8, 14, 14, 32, 64, (3, 3, 3), None, False),
+    "4f_b2b":     (8, 8, 14, 14, 32, 128, (3, 3, 3), None, False),
+    "5b_b2b":     (88, 8, 7, 7, 32, 128, (3, 3, 3), None, False),
     "3b_b1b":     (8, 16, 28, 28, 96, 128, (3, 3, 3), None, False),
     "3c_b1b":     (8, 16, 28, 28, 128, 192, (3, 3, 3), None, False),
     "4f_b1b":     (8, 8, 14, 14, 160, 320, (3, 3, 3), None, False),
@@ -32,7 +37,8 @@ for name in names:
     out = Act(torch.empty(N, T, H, W, Cout, device="cuda", dtype=torch.float16))
     r = Act(torch.randn(N, T, H, W, Cout, device="cuda").half()) if res else None
     sc = torch.ones(Cout, device="cuda"); sh = torch.zeros(Cout, device="cuda")
-    f = lambda: E.conv(x, w, sc, sh, out, k, (1, 1, 1), pad, True, r)
+    am = int(os.environ['CB_AMODE']) if os.environ.get('CB_AMODE') and k != (1, 1, 1) else None
+    f = lambda: E.conv(x, w, sc, sh, out, k, (1, 1, 1), pad, True, r, a_mode=am)
     for _ in range(3): f()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
