@@ -269,7 +269,7 @@ def run_ours(args):
         "config": {"workload": "C4: full STEP inference, two_branch, 11 proposals, max_iter=3, batch 8/GPU, "
                                "T=32, 224x224 (BASELINE.json configs[3])", "batch_per_gpu": B,
                    "global_batch": B * world, "proposals": W["N"], "l2": "inputs+activations > L2 (batch = 154 MB fp32)",
-                   "a_mode": os.environ.get("STEP_B200_AMODE", "im2col"), "cuda_graph": not args.no_graph,
+                   "a_mode": os.environ.get("STEP_B200_AMODE", "best"), "cuda_graph": not args.no_graph,
                    "batches_in_flight": n_run,
                    "parallelism": "clip-parallel x%d" % world},
         "e2e": {"value": round(total_clips / (ms_e2e * 1e-3), 3), "unit": "clips/s",

@@ -152,7 +152,8 @@ typedef struct {
   int res_ld, res_coff;
   void* y;
   int a_mode;                /* f16 path: 0 auto, 1 linear (1x1x1 only), 2 box tiles, 3 TMA im2col,
-                                4 input patch staged in shared memory (stride 1, Cin in {16,32,64}, Cout <= 128), 9 SIMT */
+                                4 input patch staged in shared memory (stride 1, Cin in {16,32,64}, Cout <= 256),
+                                5 best of 3 / 4 per layer shape, 9 SIMT */
   /* Horizontally fused 1x1x1 layers that share an input (Mixed.branch_0 / branch_1[0] / branch_2[0],
    * i3dpt.py:133-147): output channels [0, split[0]) go to y, [split[0], split[1]) to y_extra[0],
    * [split[1], Cout) to y_extra[1], each with its own channel stride / offset.  n_splits = 0: plain conv.

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libstep_b200.so")
 
 F32, F16 = 0, 1
 EXT_NONE, EXT_PREDICT, EXT_EXTRAPOLATE, EXT_MEAN = 0, 1, 2, 3
-A_AUTO, A_LINEAR, A_BOX, A_IM2COL, A_HALO, A_SIMT = 0, 1, 2, 3, 4, 9
+A_AUTO, A_LINEAR, A_BOX, A_IM2COL, A_HALO, A_BEST, A_SIMT = 0, 1, 2, 3, 4, 5, 9
 
 _lib = None
 

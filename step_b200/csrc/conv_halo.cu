@@ -62,9 +62,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* pfull_bar = empty_bar + kHaloMaxStages;    // patch landed
   uint64_t* tfull_bar = pfull_bar + 1;                 // all MMAs retired: accumulators ready, patch reusable
   uint32_t* tmem_ptr_s = (uint32_t*)(tfull_bar + 1);
-  float* s_scale = (float*)(smem_raw + 512);           // [BN <= 128]
-  float* s_shift = s_scale + 128;
-  uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 512 + 1024 + 1023) & ~(uintptr_t)1023);
+  float* s_scale = (float*)(smem_raw + 512);           // [BN <= 256]
+  float* s_shift = s_scale + 256;
+  uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 512 + 2048 + 1023) & ~(uintptr_t)1023);
   uint8_t* patch = ring + (size_t)g.n_stages * g.b_bytes;   // 1024-aligned: b_bytes is a multiple of 1024
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -211,7 +211,7 @@ static HaloEncodeTiledFn g_halo_encode = nullptr;
 bool conv3d_halo_supported(const step_conv_params* p) {
   const int taps = p->KT * p->KH * p->KW;
   return p->dtype == STEP_F16 && taps > 1 && (p->Cin == 16 || p->Cin == 32 || p->Cin == 64) && p->in_ld % 8 == 0 &&
-         p->Cout % 8 == 0 && p->Cout <= 128 && !p->residual && p->n_splits == 0 && p->KT <= 8 && p->KH <= 8 && p->KW <= 8 &&
+         p->Cout % 8 == 0 && p->Cout <= 256 && !p->residual && p->n_splits == 0 && p->KT <= 8 && p->KH <= 8 && p->KW <= 8 &&
          p->OT == p->T && p->OH == p->H && p->OW == p->W;
 }
 
@@ -277,7 +277,7 @@ int conv3d_halo_launch(const step_conv_params* p, step_stream_t stream) {
       if (tt_env > 0 && tt != tt_env && !(tt == 1)) continue;
       const long patch = (long)(tt + g.KT - 1) * (kHaloTH + g.KH - 1) * (kHaloTW + g.KW - 1) * row;
       const long stage = 4L * tt * (g.BN / 32) * 2048;
-      const long room = smem_cap - 512 - 2048 - ((patch > stage ? patch : stage) + 1023) / 1024 * 1024;
+      const long room = smem_cap - 512 - 3072 - ((patch > stage ? patch : stage) + 1023) / 1024 * 1024;
       if (room < (g.taps < 4 ? g.taps : 4) * (long)g.BN * row) continue;
       // prefer the larger tile unless more than a quarter of the computed planes would fall past the end
       const int groups = (p->OT + tt - 1) / tt;
@@ -293,7 +293,7 @@ int conv3d_halo_launch(const step_conv_params* p, step_stream_t stream) {
   g.b_bytes = g.BN * row;
   const long staging = 4L * g.TT * (g.BN / 32) * 2048;
   const long patch_area = ((g.patch_bytes > staging ? g.patch_bytes : staging) + 1023) / 1024 * 1024;
-  g.n_stages = (int)(((two_ctas ? (long)kHaloSmemMax / 2 - 1024 : (long)kHaloSmemMax) - 512 - 2048 - patch_area) / g.b_bytes);
+  g.n_stages = (int)(((two_ctas ? (long)kHaloSmemMax / 2 - 1024 : (long)kHaloSmemMax) - 512 - 3072 - patch_area) / g.b_bytes);
   STEP_CHECK_ARG(g.n_stages >= 2, "conv3d(halo): patch of %d bytes leaves no room for the weight ring", g.patch_bytes);
   if (g.n_stages > kHaloMaxStages) g.n_stages = kHaloMaxStages;
   if (const char* e = getenv("STEP_B200_HALO_STAGES")) { int v = atoi(e); if (v >= 2 && v < g.n_stages) g.n_stages = v; }
@@ -333,7 +333,7 @@ int conv3d_halo_launch(const step_conv_params* p, step_stream_t stream) {
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(STEP_E_DRIVER, "conv3d(halo): tensor map (output) encode failed: CUresult %d", (int)cr);
   }
-  const size_t smem = 512 + 1024 + 1024 + (size_t)g.n_stages * g.b_bytes + (size_t)patch_area;
+  const size_t smem = 512 + 2048 + 1024 + (size_t)g.n_stages * g.b_bytes + (size_t)patch_area;
   STEP_CHECK_ARG(smem <= (size_t)kHaloSmemMax, "conv3d(halo): %zu bytes of shared memory", smem);
   if (BK == 64) return launch_halo<64>(ma, mb, my, g, smem, (unsigned)ctas, p, cu(stream));
   if (BK == 32) return launch_halo<32>(ma, mb, my, g, smem, (unsigned)ctas, p, cu(stream));

@@ -44,7 +44,7 @@ struct ConvGeom {
   int BN, n_tiles;              // N tile (multiple of 16) and count
   int n_stages;                 // smem pipeline depth used by the one-tile-per-CTA kernel
   int n_stages_p, mh, tmem_bufs;  // persistent kernel: pipeline depth, 128-row halves per tile, accumulator sets
-  int res_tma;                    // residual tile fetched by TMA into shared memory (LINEAR mode, BN % 64 == 0)
+  int res_tma, res_bufs;          // residual tile fetched by TMA into shared memory (LINEAR mode, BN % 64 == 0); 1 | 2 buffers
   int cluster;                    // 1, or 2: CTA pairs sharing the weight tile by TMA multicast
   int tma_store;                  // epilogue writes 32-row x 16-column slabs with bulk tensor stores (linear M)
   int col_split;                  // mh == 1: columns [0, col_split) -> epilogue warps 2..5, the rest -> warps 6..9
@@ -400,8 +400,9 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         const int n0 = tile_n0(tile);
         if (res_tma) {
           // residual tile of this output tile (two_branch.py:79-81): coalesced, asynchronous, swizzled like an operand
-          const int rb = pit & 1;
-          mbar_wait(&rempty_bar[rb], (((uint32_t)pit >> 1) & 1u) ^ 1u);
+          const int rb = g.res_bufs == 2 ? (pit & 1) : 0;
+          const uint32_t ruse = (uint32_t)(g.res_bufs == 2 ? (pit >> 1) : pit);
+          mbar_wait(&rempty_bar[rb], (ruse & 1u) ^ 1u);
           mbar_expect_tx(&rfull_bar[rb], (uint32_t)(res_boxes * kBM * 128));
           for (int j = 0; j < res_boxes; ++j)
             tma_load_2d(&map_r, &rfull_bar[rb], rbuf + ((size_t)rb * res_boxes + j) * (kBM * 128), n0 + j * 64, mt * kBM);
@@ -528,8 +529,9 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(buf * mh + hsel) * ncols + (uint32_t)col0;
       const __half* rrow = (kHasRes && pix >= 0) ? residual + (size_t)pix * g.res_ld + g.res_coff + nbase : nullptr;
-      const uint8_t* rtile = rbuf + (size_t)(it & 1) * res_boxes * (kBM * 128);
-      if (res_tma) mbar_wait(&rfull_bar[it & 1], ((uint32_t)it >> 1) & 1u);
+      const int rb = g.res_bufs == 2 ? (it & 1) : 0;
+      const uint8_t* rtile = rbuf + (size_t)rb * res_boxes * (kBM * 128);
+      if (res_tma) mbar_wait(&rfull_bar[rb], (uint32_t)(g.res_bufs == 2 ? (it >> 1) : it) & 1u);
       if (tma_st) {
         // 32-column passes: TMEM -> registers -> scale/shift/residual/ReLU -> fp16 slab -> bulk tensor stores.  The slab
         // is two 16-column halves ([32 rows][32 B], 32B-swizzled); a half never straddles a destination boundary (splits
@@ -684,7 +686,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       }
       if (res_tma) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&rempty_bar[it & 1]);
+        if (lane == 0) mbar_arrive(&rempty_bar[rb]);
       }
     }
     if (tma_st && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // slabs are read, writes are done
@@ -832,7 +834,11 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   const bool persist = conv_variant() == 3 || (conv_variant() == 2 && taps == 1);
   {
     // N tile: as wide as the accumulator allows -- every N tile re-reads the whole A operand through L2.
-    const int cap = (persist && !p->residual) ? kMaxBNP : (p->residual ? kMaxBNRes : kMaxBN);
+    int cap = (persist && !p->residual) ? kMaxBNP : (p->residual ? kMaxBNRes : kMaxBN);
+    // STEP_B200_RESBN=256: 256-wide tiles with a single-buffered 64 KB residual tile.  Halves the re-reads of A but
+    // measured slower (76.6 vs 57.9 us on the 256 -> 1024 bottleneck exit), so the narrow tile stays the default.
+    if (persist && p->residual && p->Cout % 256 == 0 && mode == A_LINEAR && getenv("STEP_B200_RESBN") && atoi(getenv("STEP_B200_RESBN")) == 256)
+      cap = 256;
     g.n_tiles = (p->Cout + cap - 1) / cap;
     g.BN = (((p->Cout + g.n_tiles - 1) / g.n_tiles) + 15) / 16 * 16;
     g.n_stages = g.BN > 128 ? 2 : 3;
@@ -931,7 +937,8 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
     while (ncols < g.BN) ncols <<= 1;
     g.tmem_bufs = (g.mh * ncols * 2 <= 512) ? 2 : 1;
     g.res_tma = (persist && p->residual && g.mh == 1 && mode == A_LINEAR && g.BN % 64 == 0 && p->Cout % 64 == 0) ? 1 : 0;
-    const size_t res_bytes = g.res_tma ? (size_t)2 * (g.BN / 64) * kBM * 128 + 1024 : 0;
+    g.res_bufs = g.BN > 128 ? 1 : 2;
+    const size_t res_bytes = g.res_tma ? (size_t)g.res_bufs * (g.BN / 64) * kBM * 128 + 1024 : 0;
     const size_t budget = 227 * 1024 - kBookBytesP - 1024 - (size_t)kEpiWarps * kSlabBytes - res_bytes;
     const size_t stage_bytes = (size_t)g.mh * kBM * BK * 2 + (size_t)g.BN * BK * 2;
     int st = (int)(budget / stage_bytes);

@@ -10,10 +10,11 @@ import torch
 from . import _lib as L
 
 # Addressing mode of the fp16 implicit-GEMM for filters larger than 1x1x1 (include/step_b200.h a_mode):
-# "box" = tiled TMA boxes with zero-filled halo, "im2col" = TMA im2col mode (dense M tiles; default, both are
-# validated byte-for-byte by tests/test_gpu_conv.py::test_tma_tile_addressing).
-A_MODE = {"box": L.A_BOX, "im2col": L.A_IM2COL, "auto": L.A_AUTO, "simt": L.A_SIMT}[
-    os.environ.get("STEP_B200_AMODE", "im2col")]
+# "box" = tiled TMA boxes with zero-filled halo, "im2col" = TMA im2col mode (dense M tiles; both are validated
+# byte-for-byte by tests/test_gpu_conv.py::test_tma_tile_addressing), "halo" = input patch staged once in shared
+# memory (csrc/conv_halo.cu), "best" (default) = halo where it measures faster (thin inputs on large maps), else im2col.
+A_MODE = {"box": L.A_BOX, "im2col": L.A_IM2COL, "auto": L.A_AUTO, "simt": L.A_SIMT, "best": L.A_BEST}[
+    os.environ.get("STEP_B200_AMODE", "best")]
 
 
 # When set to a list, conv() appends (params, tensors-kept-alive) for every launch: bench.py replays
@@ -197,7 +198,7 @@ def conv(x, w_packed, scale, shift, out, k, stride=(1, 1, 1), pad_lo=None, relu=
         p.res_ld, p.res_coff = residual.ld, residual.coff
     p.y = out.buf.data_ptr()
     p.a_mode = A_MODE if a_mode is None else a_mode
-    if p.a_mode in (L.A_BOX, L.A_IM2COL) and k == (1, 1, 1):
+    if p.a_mode in (L.A_BOX, L.A_IM2COL, L.A_BEST) and k == (1, 1, 1):
         p.a_mode = L.A_AUTO
     assert (out.N, out.T, out.H, out.W) == (x.N,) + tuple(out_dims), "conv: output buffer shape mismatch"
     L.check(L.lib().step_conv3d_fwd(p, L.stream()))

@@ -347,6 +347,7 @@ HALO_CASES = [
     (1, 5, 17, 9, 16, 32, (3, 3, 3), None),           # 32-byte rows
     (1, 4, 14, 14, 64, 128, (3, 3, 3), None),         # 128-byte rows, one accumulator set per CTA
     (2, 1, 7, 7, 32, 40, (1, 3, 3), None),            # 2-D filter, Cout not a multiple of 32
+    (1, 3, 18, 16, 64, 192, (3, 3, 3), None),         # conv3d_2c_3x3 shape: 6 column passes, all 512 TMEM columns
 ]
 
 
