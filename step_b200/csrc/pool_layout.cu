@@ -207,6 +207,95 @@ __global__ void __launch_bounds__(128) maxpool3d_333_march_kernel(const T* __res
   }
 }
 
+
+// Strided windows ((1,3,3)/(1,2,2) after the stem and conv 2c, (3,3,3)/(2,2,2) between mixed_3 and mixed_4,
+// i3dpt.py:191-209) with the same separable marching scheme: a thread owns WB consecutive outputs of one row and one
+// 16-byte channel vector, reduces every input plane it needs over (h, w) ONCE into a WB-vector, carries the KT - ST
+// planes two consecutive outputs share, and emits max over the KT planes.  Zero padding / ceil-mode overhang follow
+// maxpool3d_kernel above: a window that overlaps the zero padding in any dimension sees a 0.
+__device__ __forceinline__ bool pool_pad_tap(int o, int S, int P, int K, int D, int pad_hi) {
+  bool z = false;
+  for (int k = 0; k < K; ++k) {
+    const int pos = o * S + k - P;
+    z = z || pos < 0 || (pos >= D && pos < D + pad_hi);
+  }
+  return z;
+}
+
+template <typename T, int KT, int KH, int KW, int ST, int SH, int SW, int WB>
+__global__ void __launch_bounds__(128) maxpool3d_march_kernel(const T* __restrict__ x, int N, int T_, int H, int W, int C,
+                                                              int in_ld, int PT, int PH, int PW, int pad_hi_t, int pad_hi_h,
+                                                              int pad_hi_w, int OT, int OH, int OW, T* __restrict__ y,
+                                                              int out_ld, int TS) {
+  constexpr int VN = Vec16<T>::N, NC = (WB - 1) * SW + KW, CARRY = KT > ST ? KT - ST : 0;
+  const int nvec = C / VN, wsegs = (OW + WB - 1) / WB, tsegs = (OT + TS - 1) / TS;
+  const long long total = (long long)N * tsegs * OH * wsegs * nvec;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % nvec);
+  long long r = idx / nvec;
+  const int ws = (int)(r % wsegs); r /= wsegs;
+  const int oh = (int)(r % OH); r /= OH;
+  const int ts = (int)(r % tsegs);
+  const int n = (int)(r / tsegs);
+  const int ow0 = ws * WB, ot0 = ts * TS, ot1 = min(OT, ot0 + TS);
+  const int wbase = ow0 * SW - PW, hbase = oh * SH - PH;
+  const uint4 lo = vec_lowest<T>();
+  const bool zh = pool_pad_tap(oh, SH, PH, KH, H, pad_hi_h);
+  bool zw[WB];
+#pragma unroll
+  for (int j = 0; j < WB; ++j) zw[j] = pool_pad_tap(ow0 + j, SW, PW, KW, W, pad_hi_w);
+
+  // one input plane reduced over the (KH x KW) window of each of the WB outputs
+  auto plane = [&](int tt, uint4* dst) {
+#pragma unroll
+    for (int j = 0; j < WB; ++j) dst[j] = lo;
+    if (tt < 0 || tt >= T_) return;
+#pragma unroll
+    for (int dh = 0; dh < KH; ++dh) {
+      const int hh = hbase + dh;
+      if (hh < 0 || hh >= H) continue;
+      const T* rowp = x + (((size_t)n * T_ + tt) * H + hh) * W * in_ld + cv * VN;
+      uint4 v[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int w = wbase + c;
+        v[c] = (w >= 0 && w < W) ? *reinterpret_cast<const uint4*>(rowp + (size_t)w * in_ld) : lo;
+      }
+#pragma unroll
+      for (int j = 0; j < WB; ++j) {
+        uint4 m = v[j * SW];
+#pragma unroll
+        for (int dw = 1; dw < KW; ++dw) m = vec_max<T>(m, v[j * SW + dw]);
+        dst[j] = vec_max<T>(dst[j], m);
+      }
+    }
+  };
+
+  uint4 pl[KT][WB];
+#pragma unroll
+  for (int i = 0; i < CARRY; ++i) plane(ot0 * ST - PT + i, pl[i]);
+  for (int ot = ot0; ot < ot1; ++ot) {
+    const int tbase = ot * ST - PT;
+#pragma unroll
+    for (int i = CARRY; i < KT; ++i) plane(tbase + i, pl[i]);
+    const bool z = zh || pool_pad_tap(ot, ST, PT, KT, T_, pad_hi_t);
+    T* orow = y + ((((size_t)n * OT + ot) * OH + oh) * OW + ow0) * out_ld + cv * VN;
+#pragma unroll
+    for (int j = 0; j < WB; ++j) {
+      uint4 m = pl[0][j];
+#pragma unroll
+      for (int i = 1; i < KT; ++i) m = vec_max<T>(m, pl[i][j]);
+      if (z || zw[j]) m = vec_max<T>(m, make_uint4(0, 0, 0, 0));
+      if (ow0 + j < OW) *reinterpret_cast<uint4*>(orow + (size_t)j * out_ld) = m;
+    }
+#pragma unroll
+    for (int i = 0; i < CARRY; ++i)
+#pragma unroll
+      for (int j = 0; j < WB; ++j) pl[i][j] = pl[i + ST][j];
+  }
+}
+
 // x [A,B,P,C] (C contiguous, pixel stride ld) -> y [A, P*C]  (mean over B, fp32 accumulate in index order)
 template <typename TI, typename TO>
 __global__ void mean_mid_kernel(const TI* __restrict__ x, int A, int B, int P, int C, int ld, TO* __restrict__ y) {
@@ -549,6 +638,29 @@ extern "C" int step_maxpool3d_fwd(const void* x, int dtype, int N, int T, int H,
                                                                                                 in_ld, (float*)y, out_ld, TS);
     STEP_LAUNCH_CHECK("maxpool3d_333_march_kernel");
     return 0;
+  }
+  {
+    const char* pm = getenv("STEP_B200_POOLMARCH");
+    const bool on = !(pm && pm[0] == '0');
+    const bool k133 = KT == 1 && KH == 3 && KW == 3 && ST == 1 && SH == 2 && SW == 2;
+    const bool k333 = KT == 3 && KH == 3 && KW == 3 && ST == 2 && SH == 2 && SW == 2;
+    if (on && (k133 || k333)) {
+      const int WB = k133 ? 7 : 4;
+      const long long per_seg = (long long)N * OH * ceil_div(OW, WB) * (C / vn);
+      int TS = k133 ? 1 : OT;
+      while (TS > 2 && per_seg * ceil_div(OT, TS) < 50000) TS = (TS + 1) / 2;
+      const long long total = per_seg * ceil_div(OT, TS);
+      STEP_CHECK_ARG(ceil_div(total, 128) < (1LL << 31), "maxpool3d: too many blocks");
+      const unsigned blocks = (unsigned)ceil_div(total, 128);
+#define STEP_MARCH_GO(TT_, A, B, Cc, D, E, F, G)                                                                        \
+      maxpool3d_march_kernel<TT_, A, B, Cc, D, E, F, G><<<blocks, 128, 0, cu(stream)>>>(                               \
+          (const TT_*)x, N, T, H, W, C, in_ld, PT, PH, PW, pad_hi_t, pad_hi_h, pad_hi_w, OT, OH, OW, (TT_*)y, out_ld, TS)
+      if (dtype == STEP_F16) { if (k133) STEP_MARCH_GO(__half, 1, 3, 3, 1, 2, 2, 7); else STEP_MARCH_GO(__half, 3, 3, 3, 2, 2, 2, 4); }
+      else { if (k133) STEP_MARCH_GO(float, 1, 3, 3, 1, 2, 2, 7); else STEP_MARCH_GO(float, 3, 3, 3, 2, 2, 2, 4); }
+#undef STEP_MARCH_GO
+      STEP_LAUNCH_CHECK("maxpool3d_march_kernel");
+      return 0;
+    }
   }
   // tile: up to 4 x 8 x 8 output pixels (whole rows on the small maps), 64-byte channel chunks
   const int TW = OW < 8 ? OW : (OW % 7 == 0 ? 7 : 8), TH = OH < 8 ? OH : (OH % 7 == 0 ? 7 : 8), TT = OT < 4 ? OT : 4;
