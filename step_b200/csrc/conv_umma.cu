@@ -46,7 +46,7 @@ struct ConvGeom {
   int n_stages_p, mh, tmem_bufs;  // persistent kernel: pipeline depth, 128-row halves per tile, accumulator sets
   int res_tma, res_bufs;          // residual tile fetched by TMA into shared memory (LINEAR mode, BN % 64 == 0); 1 | 2 buffers
   int cluster;                    // 1, or 2: CTA pairs sharing the weight tile by TMA multicast
-  int tma_store;                  // epilogue writes 32-row x 16-column slabs with bulk tensor stores (linear M)
+  int tma_store, st_w;            // epilogue writes 32-row slabs with bulk tensor stores (linear M); box width 16 | 32 columns
   int col_split;                  // mh == 1: columns [0, col_split) -> epilogue warps 2..5, the rest -> warps 6..9
   int n_splits, split[2], ld_extra[2], coff_extra[2];  // fused 1x1x1 layers: extra destinations by column range
   __half* y_extra[2];
@@ -504,7 +504,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       long long m = o.m0 + row;
       return m < g.M ? m : -1;
     };
-    const bool tma_st = g.tma_store != 0;
+    const bool tma_st = g.tma_store != 0, w32 = g.st_w == 32;
     int pass = 0;                                  // bulk-store passes issued by this warp (slab double buffer)
     int it = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
@@ -587,7 +587,10 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
               }
-              store16(reinterpret_cast<__half*>(sl + (q >> 1) * 1024 + lane * 32 + (((q & 1) ^ ((lane >> 2) & 1)) << 4)), f);
+              // 16-column boxes: two halves of [32 rows][32 B], 32B swizzle.  32-column boxes: [32 rows][64 B], 64B swizzle
+              const int soff = w32 ? lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)
+                                   : (q >> 1) * 1024 + lane * 32 + (((q & 1) ^ ((lane >> 2) & 1)) << 4);
+              store16(reinterpret_cast<__half*>(sl + soff), f);
             }
           }
           if (last) tc_fence_before();
@@ -595,7 +598,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           __syncwarp();
           if (lane == 0) {
             if (last) mbar_arrive(&tempty_bar[buf]);   // accumulator fully read by this warp
-            for (int h = 0; h * 16 < cw; ++h) {
+            for (int h = 0; h * 16 < (w32 ? 16 : cw); ++h) {   // one 32-column box, or one 16-column box per half
               const int gc = nbase + cb + h * 16;
               if (gc >= g.Cout) break;
               int d = 0, ds = 0;
@@ -963,6 +966,13 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
       } else {
         g.col_split = ((g.BN / 16 + 1) / 2) * 16;
       }
+      // 32-column boxes (half the bulk-store requests) when no box can straddle a destination or the next N tile
+      g.st_w = 16;
+      if (g.tma_store && (g.n_tiles == 1 || g.BN % 32 == 0) && !(getenv("STEP_B200_STW") && atoi(getenv("STEP_B200_STW")) == 16)) {
+        bool ok = true;
+        for (int i = 0; i < p->n_splits; ++i) ok = ok && p->split[i] % 32 == 0;
+        if (ok) g.st_w = 32;
+      }
       for (int d = 0; d < 3; ++d) pl->map_y[d] = pl->map_b;   // placeholders
       if (g.tma_store) {
         STEP_CHECK_ARG(g.M < (1LL << 31), "conv3d(f16): M too large");
@@ -972,10 +982,11 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
           const int ld = d ? p->ld_extra[d - 1] : p->out_ld;
           cuuint64_t ydims[2] = {(cuuint64_t)(de - ds), (cuuint64_t)g.M};
           cuuint64_t ystr[1] = {(cuuint64_t)ld * 2};
-          cuuint32_t ybox[2] = {16, 32};
+          cuuint32_t ybox[2] = {(cuuint32_t)g.st_w, 32};
           const cuuint32_t ones2[2] = {1, 1};
           CUresult cy = g_encode_tiled(&pl->map_y[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, ydims, ystr, ybox, ones2,
-                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, g.st_w == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
           if (cy != CUDA_SUCCESS) return fail(STEP_E_DRIVER, "conv3d(f16): tensor map (output %d) encode failed: CUresult %d", d, (int)cy);
         }

@@ -368,26 +368,51 @@ __global__ void __launch_bounds__(256) roi_align_fwd_nhwc_f16_packed_kernel(cons
     for (int e = 0; e < n; ++e) { b.pos[e] = pos[e]; b.w[e] = __float2half2_rn(wt[e]); }
   }
   __syncthreads();
-  int bin = threadIdx.x / nvec, cv = threadIdx.x - bin * nvec;   // incremental (bin, cv): no per-item division
-  const int dbin = blockDim.x / nvec, dcv = blockDim.x - dbin * nvec;
+  // Gather: an item is (bin, channel vector pair): the table entry (pixel offset, merged weight) is read once for
+  // two 16-byte vectors half a row apart, and two entries are in flight per iteration (4 independent loads).
+  const bool pair = (nvec & 1) == 0;
+  const int hv = pair ? (nvec >> 1) : nvec;
+  int bin = threadIdx.x / hv, cv = threadIdx.x - bin * hv;   // incremental (bin, cv): no per-item division
+  const int dbin = blockDim.x / hv, dcv = blockDim.x - dbin * hv;
+  const __half2 z2 = __float2half2_rn(0.0f);
+  auto fma4 = [](__half2* a, __half2 w, const uint4& v) {
+    a[0] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.x), a[0]);
+    a[1] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.y), a[1]);
+    a[2] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.z), a[2]);
+    a[3] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.w), a[3]);
+  };
   while (bin < nbins) {
     const MergedBin& b = bins[bin];
-    __half2 a0 = __float2half2_rn(0.0f), a1 = a0, a2 = a0, a3 = a0;
-    const __half* fp = fbase + cv * 8;
-    for (int e = 0; e < b.n; ++e) {
-      const uint4 v = *reinterpret_cast<const uint4*>(fp + (size_t)b.pos[e] * feat_ld);
-      const __half2 w = b.w[e];
-      a0 = __hfma2(w, *reinterpret_cast<const __half2*>(&v.x), a0);
-      a1 = __hfma2(w, *reinterpret_cast<const __half2*>(&v.y), a1);
-      a2 = __hfma2(w, *reinterpret_cast<const __half2*>(&v.z), a2);
-      a3 = __hfma2(w, *reinterpret_cast<const __half2*>(&v.w), a3);
+    __half2 a[4] = {z2, z2, z2, z2}, c[4] = {z2, z2, z2, z2};
+    const __half* fp0 = fbase + cv * 8;
+    const __half* fp1 = fp0 + hv * 8;
+    const int n = b.n;
+    int e = 0;
+    for (; e + 1 < n; e += 2) {
+      const size_t o0 = (size_t)b.pos[e] * feat_ld, o1 = (size_t)b.pos[e + 1] * feat_ld;
+      const __half2 w0 = b.w[e], w1 = b.w[e + 1];
+      const uint4 v00 = *reinterpret_cast<const uint4*>(fp0 + o0);
+      const uint4 v10 = *reinterpret_cast<const uint4*>(fp0 + o1);
+      if (pair) {
+        const uint4 v01 = *reinterpret_cast<const uint4*>(fp1 + o0);
+        const uint4 v11 = *reinterpret_cast<const uint4*>(fp1 + o1);
+        fma4(c, w0, v01);
+        fma4(c, w1, v11);
+      }
+      fma4(a, w0, v00);
+      fma4(a, w1, v10);
     }
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&a0); o.y = *reinterpret_cast<uint32_t*>(&a1);
-    o.z = *reinterpret_cast<uint32_t*>(&a2); o.w = *reinterpret_cast<uint32_t*>(&a3);
-    *reinterpret_cast<uint4*>(obase + (size_t)bin * out_ld + cv * 8) = o;
+    if (e < n) {
+      const size_t o0 = (size_t)b.pos[e] * feat_ld;
+      const __half2 w0 = b.w[e];
+      fma4(a, w0, *reinterpret_cast<const uint4*>(fp0 + o0));
+      if (pair) fma4(c, w0, *reinterpret_cast<const uint4*>(fp1 + o0));
+    }
+    __half* op = obase + (size_t)bin * out_ld + cv * 8;
+    *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(a);
+    if (pair) *reinterpret_cast<uint4*>(op + hv * 8) = *reinterpret_cast<const uint4*>(c);
     bin += dbin; cv += dcv;
-    if (cv >= nvec) { cv -= nvec; ++bin; }
+    if (cv >= hv) { cv -= hv; ++bin; }
   }
 }
 
