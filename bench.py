@@ -245,11 +245,27 @@ def run_ours(args):
         replay()
         ms_conv = timed_local(torch, replay, max(3, args.steps))
         pk = peaks()
+        # algorithmic bytes of the same launches: input + weights + output (+ residual), fp16
+        alg_bytes = 0
+        for q, _ in rec:
+            taps = q.KT * q.KH * q.KW
+            alg_bytes += 2 * (q.N * q.T * q.H * q.W * q.Cin + q.Cout * taps * q.Cin +
+                              q.N * q.OT * q.OH * q.OW * q.Cout * (2 if q.residual else 1))
+        # DRAM bytes the same launches moved in one ncu capture (tools/gpu_profiles.sh -> profiles/r1_conv_traffic.json)
+        traffic = None
+        tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_conv_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_step")
+            except Exception:
+                traffic = None
         flops = ALG_GFLOP_PER_CLIP * 1e9 * B
         achieved = flops / (ms_conv / max(3, args.steps) * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_umma_kernel", "achieved": round(achieved, 2),
+        roof = {"bound": "tensor", "kernel": "tcgen05 conv class: conv_umma_kernel + conv_umma_persist_kernel + conv_halo_kernel",
+                "achieved": round(achieved, 2),
                 "peak": pk["tflops"], "peak_source": pk["src"] + " bf16 sustained", "unit": "TFLOP/s",
-                "frac": round(achieved / pk["tflops"], 4), "traffic": None,
+                "frac": round(achieved / pk["tflops"], 4), "traffic": traffic, "traffic_unit": "DRAM bytes per step, all conv launches (ncu)",
+                "algorithmic_bytes_per_step": int(alg_bytes),
                 "launches_per_step": len(rec), "ms_per_step_in_kernel": round(ms_conv / max(3, args.steps), 4),
                 "algorithmic_gflop_per_step": round(flops / 1e9, 1)}
         del rec

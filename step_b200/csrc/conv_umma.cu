@@ -134,13 +134,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       const uint32_t tx_bytes = (uint32_t)(g.a_bytes + b_bytes);
       int stage = 0; uint32_t phase = 0;
+      int kw = 0, kh = 0, kt = 0;                  // filter tap, advanced incrementally (no divisions in the loop)
+      uint8_t* a_dst = sA;
+      uint8_t* b_dst = sB;
       for (int tap = 0; tap < g.taps; ++tap) {
-        const int kw = tap % g.KW, kh = (tap / g.KW) % g.KH, kt = tap / (g.KW * g.KH);
         for (int kc = 0; kc < g.kblocks_per_tap; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], tx_bytes);
-          void* a_dst = sA + stage * kABytes;
-          void* b_dst = sB + stage * b_bytes;
           const int c0 = kc * BK;
           if (g.mode == A_LINEAR) {
             tma_load_2d(&map_a, &full_bar[stage], a_dst, c0, (int)m0);
@@ -150,30 +150,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tma_load_im2col_5d(&map_a, &full_bar[stage], a_dst, c0, iw, ih, it, in_, (uint16_t)kw, (uint16_t)kh, (uint16_t)kt);
           }
           tma_load_3d(&map_b, &full_bar[stage], b_dst, c0, tap, n0);
-          if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+          a_dst += kABytes; b_dst += b_bytes;
+          if (++stage == g.n_stages) { stage = 0; phase ^= 1; a_dst = sA; b_dst = sB; }
         }
+        if (++kw == g.KW) { kw = 0; if (++kh == g.KH) { kh = 0; ++kt; } }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    int stage = 0; uint32_t phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_addr = smem_u32(sA + stage * kABytes), b_addr = smem_u32(sB + stage * b_bytes);
+    // One thread runs the whole loop.  With a narrow N tile an MMA occupies the tensor pipe for as little as 32-64
+    // cycles, so the per-k-block issue path must be a handful of instructions: descriptor high words are constants,
+    // the low words (shared-memory address >> 4) advance by adds (measured on the stem: csrc/conv_halo.cu).
+    if (elect_one()) {
+      constexpr uint64_t kLayout = BK == 64 ? 2 : (BK == 32 ? 4 : 6);
+      constexpr uint64_t kDescHi = ((uint64_t)((8 * BK * 2) >> 4) << 32) | (1ULL << 46) | (kLayout << 61);
+      const uint32_t a_lo0 = (smem_u32(sA) & 0x3FFFF) >> 4, b_lo0 = (smem_u32(sB) & 0x3FFFF) >> 4;
+      const uint32_t a_step = (uint32_t)kABytes >> 4, b_step = (uint32_t)b_bytes >> 4, idesc = g.idesc;
+      uint32_t a_lo = a_lo0, b_lo = b_lo0;
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t acc0 = kb ? 1u : 0u;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the swizzle atom
-          umma_f16(tmem_base, make_smem_desc<BK>(a_addr + k * 32), make_smem_desc<BK>(b_addr + k * 32), g.idesc,
-                   (kb | k) ? 1u : 0u);
-        }
-        umma_commit(&empty_bar[stage]);                   // frees the smem stage when the MMAs retire
-        if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulator complete
+        for (int k = 0; k < BK / 16; ++k)          // 16 elements (32 bytes) along K inside the swizzle atom per step
+          umma_f16(tmem_base, kDescHi | (uint64_t)(a_lo + 2 * k), kDescHi | (uint64_t)(b_lo + 2 * k), idesc, k ? 1u : acc0);
+        umma_commit(&empty_bar[stage]);            // frees the smem stage when the MMAs retire
+        a_lo += a_step; b_lo += b_step;
+        if (++stage == g.n_stages) { stage = 0; phase ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
       }
-      __syncwarp();
-      if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+      umma_commit(tmem_full_bar);                  // accumulator complete
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int lane_grp = warp & 3;  // TMEM lane quarter this warp may access
@@ -450,34 +458,43 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    int stage = 0; uint32_t phase = 0;
-    int it = 0;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
-      const int buf = nbuf == 2 ? (it & 1) : 0;
-      const uint32_t use = (uint32_t)(nbuf == 2 ? (it >> 1) : it);
-      mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // the epilogue has drained this accumulator set
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * mh) * ncols;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // one thread runs the whole loop; descriptor high words are constants, low words advance by adds (see above)
+    if (elect_one()) {
+      constexpr uint64_t kLayout = BK == 64 ? 2 : (BK == 32 ? 4 : 6);
+      constexpr uint64_t kDescHi = ((uint64_t)((8 * BK * 2) >> 4) << 32) | (1ULL << 46) | (kLayout << 61);
+      const uint32_t st_lo0 = (smem_u32(smem) & 0x3FFFF) >> 4, st_step = (uint32_t)stage_bytes >> 4;
+      const uint32_t a_half = (uint32_t)kABytes >> 4, b_off = (uint32_t)(mh * kABytes) >> 4, idesc = g.idesc;
+      uint32_t st_lo = st_lo0;
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
+        const int buf = nbuf == 2 ? (it & 1) : 0;
+        const uint32_t use = (uint32_t)(nbuf == 2 ? (it >> 1) : it);
+        mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // the epilogue has drained this accumulator set
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = st + mh * kABytes;
-          for (int h = 0; h < mh; ++h) {
-            const uint32_t a_addr = st + h * kABytes;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * mh) * ncols;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t acc0 = kb ? 1u : 0u;
+          const uint32_t b_lo = st_lo + b_off;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(tmem_d, kDescHi | (uint64_t)(st_lo + 2 * k), kDescHi | (uint64_t)(b_lo + 2 * k), idesc, k ? 1u : acc0);
+          if (mh == 2) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_f16(tmem_d + (uint32_t)h * ncols, make_smem_desc<BK>(a_addr + k * 32), make_smem_desc<BK>(b_addr + k * 32),
-                       g.idesc, (kb | k) ? 1u : 0u);
+              umma_f16(tmem_d + ncols, kDescHi | (uint64_t)(st_lo + a_half + 2 * k), kDescHi | (uint64_t)(b_lo + 2 * k), idesc,
+                       k ? 1u : acc0);
           }
           if (cl2) umma_commit_mcast(&empty_bar[stage], (uint16_t)3); else umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[buf]);
+          st_lo += st_step;
+          if (++stage == g.n_stages_p) { stage = 0; phase ^= 1; st_lo = st_lo0; }
         }
-        __syncwarp();
-        if (++stage == g.n_stages_p) { stage = 0; phase ^= 1; }
+        umma_commit(&tfull_bar[buf]);
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..9) =====================
     // mh == 2: warp = (lane quarter, row half), all BN columns.  mh == 1: warp = (lane quarter, column half).

@@ -41,11 +41,24 @@ cfg = synth.make_cfg(fp16=True)
 base = step_b200.BaseNet(cfg); base.load_state_dict(synth.base_net_state_dict()); base = base.cuda().eval()
 x = synth.make_clips(4, 32, 224, 224).cuda()
 with torch.no_grad():
-    ms = timeit(lambda: base.forward_act(x), reps=20, warm=5)
+    ms_eager = timeit(lambda: base.forward_act(x), reps=20, warm=5)
+    # the same launches as one CUDA graph (how StepRunner / bench.py run them): no Python between kernels
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        base.forward_act(x)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        feat_static = base.forward_act(x)
+    ms = timeit(graph.replay, reps=20, warm=5)
 gflop = 109.29 * 4
-out["C2_trunk_b4_fp16"] = {"ms": round(ms, 3), "clips_per_s": round(4 / ms * 1e3, 1), "tflops": round(gflop / ms, 1),
+out["C2_trunk_b4_fp16"] = {"ms": round(ms, 3), "ms_eager": round(ms_eager, 3), "clips_per_s": round(4 / ms * 1e3, 1),
+                           "tflops": round(gflop / ms, 1),
                            "frac_of_bf16_sustained": round(gflop / ms / PEAKS["bf16_tflops_sustained"], 3),
-                           "algorithmic_gflop": gflop, "note": "eager launches, inputs 77 MB fp32 (> L2 with activations)"}
+                           "algorithmic_gflop": gflop,
+                           "note": "one CUDA graph per forward (ms_eager: Python-launched), inputs 77 MB fp32 (> L2 with activations)"}
 
 # ---- C3a: ROIAlign ----------------------------------------------------------------------------
 rois_np, boxes_np, scores_np = synth.make_c3_rois()
