@@ -41,6 +41,7 @@ struct ConvGeom {
   int mode;
   int taps, KT, KH, KW, PT, PH, PW;
   int kblocks_per_tap;          // ceil(Cin / BK)
+  int k_tail_steps;             // 16-channel MMA steps of a tap's last channel block that hold real channels
   int BN, n_tiles;              // N tile (multiple of 16) and count
   int n_stages;                 // smem pipeline depth used by the one-tile-per-CTA kernel
   int n_stages_p, mh, tmem_bufs;  // persistent kernel: pipeline depth, 128-row halves per tile, accumulator sets
@@ -168,13 +169,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t a_step = (uint32_t)kABytes >> 4, b_step = (uint32_t)b_bytes >> 4, idesc = g.idesc;
       uint32_t a_lo = a_lo0, b_lo = b_lo0;
       int stage = 0; uint32_t phase = 0;
+      int kc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t acc0 = kb ? 1u : 0u;
+        const int nk = (kc == g.kblocks_per_tap - 1) ? g.k_tail_steps : BK / 16;   // zero-filled channel tail: no MMA
+        if (++kc == g.kblocks_per_tap) kc = 0;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)          // 16 elements (32 bytes) along K inside the swizzle atom per step
-          umma_f16(tmem_base, kDescHi | (uint64_t)(a_lo + 2 * k), kDescHi | (uint64_t)(b_lo + 2 * k), idesc, k ? 1u : acc0);
+          if (k < nk)
+            umma_f16(tmem_base, kDescHi | (uint64_t)(a_lo + 2 * k), kDescHi | (uint64_t)(b_lo + 2 * k), idesc, k ? 1u : acc0);
         umma_commit(&empty_bar[stage]);            // frees the smem stage when the MMAs retire
         a_lo += a_step; b_lo += b_step;
         if (++stage == g.n_stages) { stage = 0; phase ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
@@ -473,19 +478,24 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // the epilogue has drained this accumulator set
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * mh) * ncols;
+        int kc = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t acc0 = kb ? 1u : 0u;
           const uint32_t b_lo = st_lo + b_off;
+          const int nk = (kc == g.kblocks_per_tap - 1) ? g.k_tail_steps : BK / 16;   // zero-filled channel tail: no MMA
+          if (++kc == g.kblocks_per_tap) kc = 0;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_f16(tmem_d, kDescHi | (uint64_t)(st_lo + 2 * k), kDescHi | (uint64_t)(b_lo + 2 * k), idesc, k ? 1u : acc0);
+            if (k < nk)
+              umma_f16(tmem_d, kDescHi | (uint64_t)(st_lo + 2 * k), kDescHi | (uint64_t)(b_lo + 2 * k), idesc, k ? 1u : acc0);
           if (mh == 2) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_f16(tmem_d + ncols, kDescHi | (uint64_t)(st_lo + a_half + 2 * k), kDescHi | (uint64_t)(b_lo + 2 * k), idesc,
-                       k ? 1u : acc0);
+              if (k < nk)
+                umma_f16(tmem_d + ncols, kDescHi | (uint64_t)(st_lo + a_half + 2 * k), kDescHi | (uint64_t)(b_lo + 2 * k), idesc,
+                         k ? 1u : acc0);
           }
           if (cl2) umma_commit_mcast(&empty_bar[stage], (uint16_t)3); else umma_commit(&empty_bar[stage]);
           st_lo += st_step;
@@ -786,6 +796,9 @@ static CUtensorMapSwizzle swizzle_for(int BK) {
 }
 
 static int pick_bk(int Cin) {
+  // STEP_B200_BKPOL=1: widest block that the channel count reaches -- the MMA loop skips the zero-filled 16-channel
+  // steps of a tap's last block and TMA does not fetch them, so padding inside a block is (nearly) free
+  if (const char* e = getenv("STEP_B200_BKPOL")) { if (e[0] == '1') return Cin > 32 ? 64 : (Cin > 16 ? 32 : 16); }
   int best = 64; long best_cost = -1;
   const int cands[3] = {64, 32, 16};
   for (int i = 0; i < 3; ++i) {
@@ -850,6 +863,7 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   pl->BK = pick_bk(p->Cin);
   const int BK = pl->BK;
   g.kblocks_per_tap = (p->Cin + BK - 1) / BK;
+  g.k_tail_steps = (p->Cin - (g.kblocks_per_tap - 1) * BK + 15) / 16;   // the rest of the block is TMA zero fill: skip it
   long long m128 = 0;   // number of 128-row M tiles (filled in below once the A mode is known)
   const bool persist = conv_variant() == 3 || (conv_variant() == 2 && taps == 1);
   {

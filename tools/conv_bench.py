@@ -17,6 +17,9 @@ LAYERS = {
     "5b_b2b":     (88, 8, 7, 7, 32, 128, (3, 3, 3), None, False),
     "3b_b1b":     (8, 16, 28, 28, 96, 128, (3, 3, 3), None, False),
     "3c_b1b":     (8, 16, 28, 28, 128, 192, (3, 3, 3), None, False),
+    "4c_b1b":     (8, 8, 14, 14, 112, 224, (3, 3, 3), None, False),
+    "4e_b1b":     (8, 8, 14, 14, 144, 288, (3, 3, 3), None, False),
+    "5c_b2b":     (88, 8, 7, 7, 48, 128, (3, 3, 3), None, False),
     "4f_b1b":     (8, 8, 14, 14, 160, 320, (3, 3, 3), None, False),
     "5b_b1b":     (88, 8, 7, 7, 160, 320, (3, 3, 3), None, False),
     "5c_b1b":     (88, 8, 7, 7, 192, 384, (3, 3, 3), None, False),
