@@ -875,7 +875,8 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
       cap = 256;
     g.n_tiles = (p->Cout + cap - 1) / cap;
     g.BN = (((p->Cout + g.n_tiles - 1) / g.n_tiles) + 15) / 16 * 16;
-    g.n_stages = g.BN > 128 ? 2 : 3;
+    // three stages whenever two CTAs of them still fit one SM (<= 112 KB each incl. bookkeeping), else two
+    g.n_stages = (kBookBytes + 1024 + 3L * (kBM * BK * 2 + g.BN * BK * 2) <= 112 * 1024) ? 3 : 2;
   }
   g.Cout = p->Cout; g.out_ld = p->out_ld; g.out_coff = p->out_coff; g.res_ld = p->res_ld; g.res_coff = p->res_coff;
   g.relu = p->relu;
@@ -1055,7 +1056,7 @@ template <int BK, bool kHasRes>
 static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv3d(f16): smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
