@@ -874,6 +874,17 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
     if (persist && p->residual && p->Cout % 256 == 0 && mode == A_LINEAR && getenv("STEP_B200_RESBN") && atoi(getenv("STEP_B200_RESBN")) == 256)
       cap = 256;
     g.n_tiles = (p->Cout + cap - 1) / cap;
+    // STEP_B200_NSPLIT=1 (one tile per CTA kernel, k > 1): when there are fewer M tiles than SMs, split N further so
+    // that ~2 CTAs land on every SM.  Measured worse on the mixed_4 layers (4e 56 -> 78 us, 4f 55 -> 73 us: every extra
+    // N tile re-pulls A through TMA and the layers are bound by exactly that), so it stays an experiment switch.
+    if (!persist && taps > 1 && getenv("STEP_B200_NSPLIT") && getenv("STEP_B200_NSPLIT")[0] == '1') {
+      const long long mt = ((long long)p->N * p->OT * p->OH * p->OW + kBM - 1) / kBM;
+      if (mt < kNumSMs) {
+        int want = (int)((2 * kNumSMs + mt - 1) / mt);
+        while (want > g.n_tiles && (p->Cout + want - 1) / want < 64) --want;   // keep N tiles >= 64 columns
+        if (want > g.n_tiles) g.n_tiles = want;
+      }
+    }
     g.BN = (((p->Cout + g.n_tiles - 1) / g.n_tiles) + 15) / 16 * 16;
     // three stages whenever two CTAs of them still fit one SM (<= 112 KB each incl. bookkeeping), else two
     g.n_stages = (kBookBytes + 1024 + 3L * (kBM * BK * 2 + g.BN * BK * 2) <= 112 * 1024) ? 3 : 2;
