@@ -299,9 +299,58 @@ __global__ void __launch_bounds__(256) roi_align_fwd_nhwc_kernel(const T* __rest
 constexpr int kMaxMerged = 16;
 struct MergedBin {
   int n;
-  int pos[kMaxMerged];
-  __half2 w[kMaxMerged];
+  int pad;
+  uint2 e[kMaxMerged];   // .x = element offset of the pixel row (pixel index * feat_ld), .y = merged weight as half2 bits
 };
+
+__device__ __forceinline__ void hfma2x4(__half2* a, __half2 w, const uint4& v) {
+  a[0] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.x), a[0]);
+  a[1] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.y), a[1]);
+  a[2] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.z), a[2]);
+  a[3] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.w), a[3]);
+}
+
+template <int V>
+__device__ __forceinline__ void roi_gather_items(const MergedBin* bins, int nbins, int nvec, const __half* fbase, __half* obase,
+                                                 int out_ld) {
+  const int hv = nvec / V;
+  int bin = threadIdx.x / hv, cv = threadIdx.x - bin * hv;   // incremental (bin, cv): no per-item division
+  const int dbin = blockDim.x / hv, dcv = blockDim.x - dbin * hv;
+  const __half2 z2 = __float2half2_rn(0.0f);
+  while (bin < nbins) {
+    const MergedBin& b = bins[bin];
+    __half2 acc[V][4];
+#pragma unroll
+    for (int u = 0; u < V; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = z2;
+    const __half* fp = fbase + cv * 8;
+    const int n = b.n;
+    int e = 0;
+    for (; e + 1 < n; e += 2) {
+      const uint2 e0 = b.e[e], e1 = b.e[e + 1];          // one 8-byte shared load per entry
+      const __half2 w0 = *reinterpret_cast<const __half2*>(&e0.y), w1 = *reinterpret_cast<const __half2*>(&e1.y);
+      uint4 v0[V], v1[V];
+#pragma unroll
+      for (int u = 0; u < V; ++u) {
+        v0[u] = *reinterpret_cast<const uint4*>(fp + e0.x + u * hv * 8);
+        v1[u] = *reinterpret_cast<const uint4*>(fp + e1.x + u * hv * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < V; ++u) { hfma2x4(acc[u], w0, v0[u]); hfma2x4(acc[u], w1, v1[u]); }
+    }
+    if (e < n) {
+      const uint2 e0 = b.e[e];
+      const __half2 w0 = *reinterpret_cast<const __half2*>(&e0.y);
+#pragma unroll
+      for (int u = 0; u < V; ++u) hfma2x4(acc[u], w0, *reinterpret_cast<const uint4*>(fp + e0.x + u * hv * 8));
+    }
+    __half* op = obase + (size_t)bin * out_ld + cv * 8;
+#pragma unroll
+    for (int u = 0; u < V; ++u) *reinterpret_cast<uint4*>(op + u * hv * 8) = *reinterpret_cast<const uint4*>(acc[u]);
+    bin += dbin; cv += dcv;
+    if (cv >= hv) { cv -= hv; ++bin; }
+  }
+}
+
 
 __global__ void __launch_bounds__(256) roi_align_fwd_nhwc_f16_packed_kernel(const __half* __restrict__ feat, int H, int W,
                                                                             int C, int feat_ld, const float* __restrict__ rois,
@@ -365,55 +414,17 @@ __global__ void __launch_bounds__(256) roi_align_fwd_nhwc_f16_packed_kernel(cons
       }
     MergedBin& b = bins[bin];
     b.n = n;
-    for (int e = 0; e < n; ++e) { b.pos[e] = pos[e]; b.w[e] = __float2half2_rn(wt[e]); }
+    for (int e = 0; e < n; ++e) {
+      const __half2 w2 = __float2half2_rn(wt[e]);
+      b.e[e] = make_uint2((unsigned)(pos[e] * feat_ld), *reinterpret_cast<const unsigned*>(&w2));
+    }
   }
   __syncthreads();
-  // Gather: an item is (bin, channel vector pair): the table entry (pixel offset, merged weight) is read once for
-  // two 16-byte vectors half a row apart, and two entries are in flight per iteration (4 independent loads).
-  const bool pair = (nvec & 1) == 0;
-  const int hv = pair ? (nvec >> 1) : nvec;
-  int bin = threadIdx.x / hv, cv = threadIdx.x - bin * hv;   // incremental (bin, cv): no per-item division
-  const int dbin = blockDim.x / hv, dcv = blockDim.x - dbin * hv;
-  const __half2 z2 = __float2half2_rn(0.0f);
-  auto fma4 = [](__half2* a, __half2 w, const uint4& v) {
-    a[0] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.x), a[0]);
-    a[1] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.y), a[1]);
-    a[2] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.z), a[2]);
-    a[3] = __hfma2(w, *reinterpret_cast<const __half2*>(&v.w), a[3]);
-  };
-  while (bin < nbins) {
-    const MergedBin& b = bins[bin];
-    __half2 a[4] = {z2, z2, z2, z2}, c[4] = {z2, z2, z2, z2};
-    const __half* fp0 = fbase + cv * 8;
-    const __half* fp1 = fp0 + hv * 8;
-    const int n = b.n;
-    int e = 0;
-    for (; e + 1 < n; e += 2) {
-      const size_t o0 = (size_t)b.pos[e] * feat_ld, o1 = (size_t)b.pos[e + 1] * feat_ld;
-      const __half2 w0 = b.w[e], w1 = b.w[e + 1];
-      const uint4 v00 = *reinterpret_cast<const uint4*>(fp0 + o0);
-      const uint4 v10 = *reinterpret_cast<const uint4*>(fp0 + o1);
-      if (pair) {
-        const uint4 v01 = *reinterpret_cast<const uint4*>(fp1 + o0);
-        const uint4 v11 = *reinterpret_cast<const uint4*>(fp1 + o1);
-        fma4(c, w0, v01);
-        fma4(c, w1, v11);
-      }
-      fma4(a, w0, v00);
-      fma4(a, w1, v10);
-    }
-    if (e < n) {
-      const size_t o0 = (size_t)b.pos[e] * feat_ld;
-      const __half2 w0 = b.w[e];
-      fma4(a, w0, *reinterpret_cast<const uint4*>(fp0 + o0));
-      if (pair) fma4(c, w0, *reinterpret_cast<const uint4*>(fp1 + o0));
-    }
-    __half* op = obase + (size_t)bin * out_ld + cv * 8;
-    *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(a);
-    if (pair) *reinterpret_cast<uint4*>(op + hv * 8) = *reinterpret_cast<const uint4*>(c);
-    bin += dbin; cv += dcv;
-    if (cv >= hv) { cv -= hv; ++bin; }
-  }
+  // Gather: an item is (bin, V channel vectors a V-th of a row apart): the 8-byte table entry (pixel offset, merged
+  // weight) is read once for V 16-byte vectors, and two entries are in flight per iteration (2V independent loads).
+  // (measured on C3: V = 2 -> 0.575 of HBM peak, V = 4 -> 0.564, V = 1 -> 0.46)
+  if ((nvec & 1) == 0) roi_gather_items<2>(bins, nbins, nvec, fbase, obase, out_ld);
+  else roi_gather_items<1>(bins, nbins, nvec, fbase, obase, out_ld);
 }
 
 template <typename T>
@@ -531,7 +542,8 @@ extern "C" int step_roi_align_fwd_nhwc(const void* feat, int dtype, int K, int H
   if (int rc = check_nhwc("roi_align_fwd_nhwc", dtype, C, feat_ld, out_ld, feat, out)) return rc;
   STEP_CHECK_ARG(roi_T == 0 || (roi_T > 0 && t_start >= 0 && t_start + roi_T <= feat_T), "roi_align_fwd_nhwc: bad frame map");
   FrameMap fm{roi_T, feat_T, t_start};
-  if (dtype == STEP_F16 && exact == 0 && (size_t)ph * pw * sizeof(MergedBin) <= 48 * 1024) {
+  if (dtype == STEP_F16 && exact == 0 && (size_t)ph * pw * sizeof(MergedBin) <= 48 * 1024 &&
+      (long long)H * W * feat_ld < (1LL << 31)) {   // table entries hold 32-bit element offsets inside one frame
     roi_align_fwd_nhwc_f16_packed_kernel<<<R, 256, (size_t)ph * pw * sizeof(MergedBin), cu(stream)>>>(
         (const __half*)feat, H, W, C, feat_ld, rois, scale, ph, pw, sampling_ratio, (__half*)out, out_ld, fm);
     STEP_LAUNCH_CHECK("roi_align_fwd_nhwc_f16_packed_kernel");
