@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -35,6 +37,15 @@ inline cudaStream_t cu(step_stream_t s) { return reinterpret_cast<cudaStream_t>(
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148;  // B200
+
+// Function attributes (dynamic shared memory limit) are per device: a process driving several GPUs (nn.DataParallel,
+// test.py:79-95 of the reference) must set them once on each.  `seen` is a per-kernel bitmask owned by the caller.
+inline bool first_use_on_device(std::atomic<unsigned long long>& seen) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ULL << (dev & 63);
+  return (seen.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+}
 
 // ---- device helpers -----------------------------------------------------------------------
 template <typename T>

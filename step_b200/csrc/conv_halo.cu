@@ -218,11 +218,10 @@ bool conv3d_halo_supported(const step_conv_params* p) {
 template <int BK, int TT>
 static int launch_halo_tt(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const HaloGeom& g, size_t smem,
                        unsigned grid, const step_conv_params* p, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_seen{0};
+  if (first_use_on_device(attr_seen)) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BK, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemMax);
     if (e != cudaSuccess) return fail((int)e, "conv_halo_kernel attribute: %s", cudaGetErrorString(e));
-    attr_done = true;
   }
   conv_halo_kernel<BK, TT><<<grid, kHaloThreads, smem, s>>>(ma, mb, my, g, p->scale, p->shift);
   STEP_LAUNCH_CHECK("conv_halo_kernel");

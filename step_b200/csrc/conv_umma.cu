@@ -1065,11 +1065,10 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
 
 template <int BK, bool kHasRes>
 static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_seen{0};
+  if (first_use_on_device(attr_seen)) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv3d(f16): smem attribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   conv_umma_kernel<BK, kHasRes><<<pl.grid, kThreads, pl.smem_bytes, s>>>(pl.map_a, pl.map_b, pl.g, p->scale, p->shift,
                                                                         (const __half*)p->residual, (__half*)p->y);
@@ -1079,11 +1078,10 @@ static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t
 
 template <int BK, bool kHasRes>
 static int launch_persist(const ConvPlan& pl, const step_conv_params* p, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_seen{0};
+  if (first_use_on_device(attr_seen)) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_persist_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv3d(f16): smem attribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   const int total = pl.persist_tiles;
   cudaLaunchConfig_t cfg = {};
