@@ -33,7 +33,7 @@ enum { A_LINEAR = 1, A_BOX = 2, A_IM2COL = 3 };
 constexpr int kBM = 128;       // UMMA M (cta_group::1)
 constexpr int kMaxBN = 256;    // <= 256 TMEM columns per CTA so two CTAs (2 x 256 = all 512 columns) share an SM
 constexpr int kMaxBNRes = 128; // residual rows are prefetched into registers: keep that to 16 x uint4
-constexpr int kStages = 3;     // BN <= 128: 3 stages of <= 32 KB; BN > 128: 2 stages of <= 48 KB (<= 96 KB per CTA)
+constexpr int kStages = 6;     // barrier slots; the plan uses 2-3 stages when two CTAs share an SM, up to 6 when a CTA is alone
 constexpr int kThreads = 192;
 constexpr int kBookBytes = (2 * kStages + 1) * 8 + 8 + 2 * kMaxBN * 4;  // barriers, tmem ptr, scale, shift
 
@@ -888,6 +888,17 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
     g.BN = (((p->Cout + g.n_tiles - 1) / g.n_tiles) + 15) / 16 * 16;
     // three stages whenever two CTAs of them still fit one SM (<= 112 KB each incl. bookkeeping), else two
     g.n_stages = (kBookBytes + 1024 + 3L * (kBM * BK * 2 + g.BN * BK * 2) <= 112 * 1024) ? 3 : 2;
+    {
+      // Small maps (mixed_4: 98 M tiles): fewer CTAs than SMs, so each CTA is alone on its SM and its own pipeline depth
+      // is all the latency hiding there is -- give it the whole shared memory (up to kStages stages).
+      const long long mt = ((long long)p->N * p->OT * p->OH * p->OW + kBM - 1) / kBM;
+      if (!persist && mode == A_IM2COL && mt * g.n_tiles <= kNumSMs && !(getenv("STEP_B200_DEEP") && getenv("STEP_B200_DEEP")[0] == '0')) {
+        const long per_stage = kBM * BK * 2 + (long)g.BN * BK * 2;
+        int st = (int)((220L * 1024 - kBookBytes - 1024) / per_stage);
+        if (st > kStages) st = kStages;
+        if (st > g.n_stages) g.n_stages = st;
+      }
+    }
   }
   g.Cout = p->Cout; g.out_ld = p->out_ld; g.out_coff = p->out_coff; g.res_ld = p->res_ld; g.res_coff = p->res_coff;
   g.relu = p->relu;
@@ -1067,7 +1078,7 @@ template <int BK, bool kHasRes>
 static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t s) {
   static std::atomic<unsigned long long> attr_seen{0};
   if (first_use_on_device(attr_seen)) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv3d(f16): smem attribute: %s", cudaGetErrorString(e));
   }
   conv_umma_kernel<BK, kHasRes><<<pl.grid, kThreads, pl.smem_bytes, s>>>(pl.map_a, pl.map_b, pl.g, p->scale, p->shift,
