@@ -173,3 +173,45 @@ def test_full_size_c4_properties():
     keep = nms(boxes, prob[:N, 0].contiguous(), 0.4)
     again = nms(boxes[keep], prob[:N, 0][keep].contiguous(), 0.4)
     assert torch.equal(again.cpu(), torch.arange(keep.numel())) and bool((keep[1:] > keep[:-1]).all())   # (4)
+
+
+@pytest.mark.parametrize("mode", ["spatial", "predict"])
+def test_ragged_and_empty_clips_match_oracle(mode):
+    """Clips with different tube counts, one of them with none (flatten_tubes skips it but still counts it,
+    tube_utils.py:214-246): frame indices, per-clip bookkeeping and the between-steps update must agree with the
+    reference arithmetic (oracle/model.py) on the fp32 path."""
+    import step_b200
+    from oracle import model as om
+    if mode == "spatial":
+        kw = dict(T=4, max_iter=2, NUM_CHUNKS={1: 1, 2: 1}, image_size=(112, 112))
+        T_in = 16
+    else:
+        kw = dict(T=3, max_iter=2, NUM_CHUNKS={1: 1, 2: 3}, temporal_mode="predict", image_size=(112, 112))
+        T_in = 36
+    cfg = synth.make_cfg(fp16=False, **kw)
+    nets = build(cfg)
+    B = 3
+    x = synth.make_clips(B, T_in, 112, 112)
+    tubes = synth.make_proposals(B, 3, cfg.T * cfg.NUM_CHUNKS[1], 112, 112)
+    tubes[1] = tubes[1][:0]
+    tubes[2] = tubes[2][:2]
+    with torch.no_grad():
+        cf = nets["base_net"](x.cuda())
+        hist, traj = step_b200.inference(cfg, cf, None, nets, cfg.max_iter, [t.copy() for t in tubes])
+        torch.cuda.synchronize()
+        sd = synth.base_net_state_dict()
+        heads = [synth.head_state_dict(100 + i, cfg) for i in range(cfg.max_iter)]
+        rhist, rtraj = om.inference(cfg, om.base_net(x, sd), None, heads, cfg.max_iter, [t.copy() for t in tubes])
+    for i, (h, r) in enumerate(zip(hist, rhist)):
+        assert list(h["tubes_nums"]) == list(r["tubes_nums"]) == [3, 0, 2]
+        assert np.abs(h["pred_prob"].float().cpu().numpy() - r["pred_prob"].numpy()).max() <= 2e-5, i
+        extends = i + 1 < cfg.max_iter and cfg.NUM_CHUNKS[i + 2] == cfg.NUM_CHUNKS[i + 1] + 2
+        loc, rloc = h["pred_loc"].cpu().numpy(), r["pred_loc"].numpy()
+        if not extends:   # the reference's CPU path validates pred_loc in place on these steps (aliasing)
+            loc, rloc = otubes.valid_tubes(loc, 112, 112), otubes.valid_tubes(rloc.copy(), 112, 112)
+        assert np.abs(loc - rloc).max() <= 2e-3, i
+        for b in range(B):
+            got, ref = traj[i][b][0], rtraj[i][b][0]
+            assert got.shape == ref.shape
+            if got.size:
+                assert np.abs(got - ref).max() <= 2e-3, (i, b)
