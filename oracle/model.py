@@ -109,7 +109,7 @@ def _bottleneck(x, sd, p, resample):
     return F.relu(o + res)
 
 
-def two_branch(global_feat, sd, T, context_feat=None, fc_dim=256, pool_size=7, cls_only=False):
+def two_branch(global_feat, sd, T, context_feat=None, fc_dim=256, pool_size=7, cls_only=False, return_logits=False):
     """two_branch.py:205-274,337 in eval mode (dropout = identity), targets=None.
     global_feat [N,T',C,7,7] -> (global_prob [N,cls], local_loc [N,T',4], first_loc, last_loc)."""
     N, Tl, C, W, H = global_feat.shape
@@ -127,7 +127,7 @@ def two_branch(global_feat, sd, T, context_feat=None, fc_dim=256, pool_size=7, c
     prob = torch.sigmoid(cls)
     if cls_only:
         z = torch.tensor([0.0])
-        return prob, z, z, z
+        return (prob, z, z, z, cls) if return_logits else (prob, z, z, z)
     lf = torch.cat([global_feat.permute(0, 2, 1, 3, 4), gconv], dim=1)
     lf = lf.permute(0, 2, 1, 3, 4).contiguous().view(N * Tl, -1, W, H)
     lf = _bottleneck(lf, sd, "local_conv.0.", True)
@@ -145,7 +145,57 @@ def two_branch(global_feat, sd, T, context_feat=None, fc_dim=256, pool_size=7, c
                              sd["neighbor_reg1.weight"], sd["neighbor_reg1.bias"]).view(N, T, -1)
     last = last + F.linear(lf.view(N, Tl, -1)[:, e0:e1].contiguous().view(-1, D),
                            sd["neighbor_reg2.weight"], sd["neighbor_reg2.bias"]).view(N, T, -1)
+    if return_logits:
+        return prob, local_loc, first, last, cls
     return prob, local_loc, first, last
+
+
+def encode_coef_t(gt, tubes):
+    """tube_utils.py:143-163 on torch tensors."""
+    def cs(b):
+        w = b[:, 2] - b[:, 0] + 1.0
+        h = b[:, 3] - b[:, 1] + 1.0
+        return b[:, 0] + 0.5 * w, b[:, 1] + 0.5 * h, w, h
+    gx, gy, gw, gh = cs(gt)
+    x, y, w, h = cs(tubes)
+    return torch.stack(((gx - x) / w, (gy - y) / h, torch.log(gw / w), torch.log(gh / h)), dim=1)
+
+
+def two_branch_losses(cls_logits, local_loc, first_loc, last_loc, tubes, targets, T, cls_only=False):
+    """two_branch.py:272-341 (training-time outputs; test infrastructure for the round-2 training path).
+    cls_logits [N,cls] (pre-sigmoid), local_loc [N,T',4], first_loc/last_loc [N,T,4], tubes [N,T',5],
+    targets [N,3,6+cls] = (first, centre, last) x (box 4 | cls mask | loc mask | labels).
+    Returns (loss_global_cls, loss_local_loc, loss_neighbor_loc), each flattened like the reference's .view(-1)."""
+    N, Tl = tubes.shape[0], tubes.shape[1]
+    chunks = int(Tl / T)
+    chunk_idx = [j * T + int(T / 2) for j in range(chunks)]
+    half_T = int(T / 2)
+    l_cls = torch.tensor(0.0)
+    l_loc = torch.tensor(0.0)
+    l_nb = torch.tensor(0.0)
+    center_t, first_t, last_t = targets[:, 1].contiguous(), targets[:, 0].contiguous(), targets[:, -1].contiguous()
+    center_tubes = tubes[:, chunk_idx[int(chunks / 2)]].contiguous()
+    first_tubes = tubes[:, chunk_idx[0]].contiguous()
+    last_tubes = tubes[:, chunk_idx[-1]].contiguous()
+    mask = center_t[:, 4].view(-1, 1)
+    if mask.sum():
+        l_cls = F.binary_cross_entropy_with_logits(cls_logits, center_t[:, 6:] * mask, reduction="none")
+    if not cls_only:
+        center_pred = local_loc[:, chunk_idx[int(chunks / 2)]].contiguous().view(N, -1)
+        first_pred = first_loc[:, half_T].contiguous().view(N, -1)
+        last_pred = last_loc[:, half_T].contiguous().view(N, -1)
+        tgt = encode_coef_t(center_t[:, :4].clone(), center_tubes.view(-1, 5)[:, 1:])
+        m = center_t[:, 5].view(-1, 1).repeat(1, 4)
+        if m.sum():
+            l = F.smooth_l1_loss(center_pred, tgt, reduction="none")
+            l_loc = torch.sum(l * m) / torch.sum(m)
+        ntgt = encode_coef_t(torch.cat([first_t[:, :4], last_t[:, :4]], dim=0),
+                             torch.cat([first_tubes.view(-1, 5)[:, 1:], last_tubes.view(-1, 5)[:, 1:]], dim=0))
+        nm = torch.cat([first_t[:, 5].view(-1, 1).repeat(1, 4), last_t[:, 5].view(-1, 1).repeat(1, 4)], dim=0)
+        if nm.sum():
+            l = F.smooth_l1_loss(torch.cat([first_pred, last_pred], dim=0), ntgt, reduction="none")
+            l_nb = torch.sum(l * nm) / torch.sum(nm)
+    return l_cls.view(-1), l_loc.view(-1), l_nb.view(-1)
 
 
 def roi_net(conv_feat, flat_tubes, pool_mode="align", pool_size=7, use_ref=True):

@@ -170,3 +170,35 @@ def make_c3_rois(n_tubes=10000, n_clips=8, Tp=8, W=224, seed=0):
     rois = np.concatenate([frame[:, :, None], np.tile(boxes[:, None, :], (1, Tp, 1))], 2).reshape(-1, 5)
     scores = rs.rand(n_tubes).astype(np.float32)
     return rois.astype(np.float32), boxes, scores
+
+
+LOSS_CASES = {"c1": (3, 1, 5, "mixed"), "c3": (3, 3, 4, "mixed"), "nomask": (3, 1, 3, "zero")}
+
+
+def make_loss_case(name, num_classes):
+    """Seeded inputs of the training-time head call `TwoBranchNet.forward(feat, None, tubes=..., targets=...)`
+    (two_branch.py:205-341): (T, feat [n,T',832,7,7], tubes [n,T',5], targets [n,3,6+cls]).  Shared by
+    tests/golden/make_golden.py (reference run) and the oracle test."""
+    T_, chunks, n, masks = LOSS_CASES[name]
+    g = torch.Generator().manual_seed(77 + n)
+    Tl = T_ * chunks
+    feat = torch.randn(n, Tl, 832, 7, 7, generator=g) * 0.5
+    x1 = torch.rand(n, Tl, generator=g) * 50
+    y1 = torch.rand(n, Tl, generator=g) * 50
+    w = 20 + torch.rand(n, Tl, generator=g) * 40
+    h = 20 + torch.rand(n, Tl, generator=g) * 40
+    tubes = torch.stack([torch.zeros(n, Tl), x1, y1, x1 + w, y1 + h], dim=2)
+    tg = torch.zeros(n, 3, 6 + num_classes)
+    gx1 = torch.rand(n, 3, generator=g) * 50
+    gy1 = torch.rand(n, 3, generator=g) * 50
+    tg[:, :, 0] = gx1
+    tg[:, :, 1] = gy1
+    tg[:, :, 2] = gx1 + 15 + torch.rand(n, 3, generator=g) * 45
+    tg[:, :, 3] = gy1 + 15 + torch.rand(n, 3, generator=g) * 45
+    if masks == "mixed":
+        tg[:, :, 4] = (torch.rand(n, 3, generator=g) > 0.3).float()
+        tg[:, :, 5] = (torch.rand(n, 3, generator=g) > 0.4).float()
+        tg[0, :, 4] = 1.0
+        tg[0, :, 5] = 1.0
+    tg[:, :, 6:] = (torch.rand(n, 3, num_classes, generator=g) > 0.9).float()
+    return T_, chunks, feat, tubes, tg

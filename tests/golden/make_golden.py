@@ -176,5 +176,27 @@ def gen_pipelines():
                  B=1, T_in=36, HW=400, N=3, context=True, store_feat=False)
 
 
+def gen_losses():
+    """TwoBranchNet.forward(targets=...) of the reference (two_branch.py:276-341): the training-time outputs.
+    Inputs are regenerated from the seed by synth.make_loss_case, so only the outputs are stored."""
+    out = {}
+    for name in synth.LOSS_CASES:
+        T_, chunks, _, _ = synth.LOSS_CASES[name]
+        cfg = synth.make_cfg(T=T_, max_iter=1, NUM_CHUNKS={1: chunks}, image_size=(112, 112))
+        net = quiet(R.models.TwoBranchNet, cfg)
+        net.load_state_dict(synth.head_state_dict(100, cfg), strict=True)
+        net.eval(); net.set_device("cpu")
+        _, _, feat, tubes, tg = synth.make_loss_case(name, cfg.num_classes)
+        with torch.no_grad():
+            prob, loc, first, last, lc, ll, ln = net(feat, None, tubes=tubes, targets=tg)
+        for k, v in (("prob", prob), ("loc", loc), ("first", first), ("last", last), ("loss_cls", lc), ("loss_loc", ll),
+                     ("loss_nb", ln), ("feat_checksum", feat.double().sum().view(1))):
+            out["%s_%s" % (name, k)] = v.numpy()
+        print("losses", name, tuple(lc.shape), float(ll), float(ln))
+    np.savez_compressed(os.path.join(OUT, "losses_cases.npz"), **out)
+
+
 if __name__ == "__main__":
-    gen_nms(); gen_roi_align(); gen_tubes(); gen_pipelines()
+    which = sys.argv[1:] or ["nms", "roi_align", "tubes", "pipelines", "losses"]
+    for w_ in which:
+        {"nms": gen_nms, "roi_align": gen_roi_align, "tubes": gen_tubes, "pipelines": gen_pipelines, "losses": gen_losses}[w_]()

@@ -124,3 +124,27 @@ def test_pipeline_oracle_matches_reference(golden, name):
         assert np.allclose(v, g["loc_valid%d" % i], rtol=1e-4, atol=1e-3)
         assert h["tubes_nums"] == g["nums%d" % i].tolist()
         assert np.allclose(np.concatenate([t[0] for t in traj[i]], 0), g["traj%d" % i], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", list(synth.LOSS_CASES))
+def test_head_losses_oracle_matches_reference(golden, name):
+    """Training-time outputs of TwoBranchNet.forward(targets=...) (two_branch.py:276-341): BCE-with-logits on the
+    centre chunk, masked smooth-L1 on encode_coef targets, neighbour smooth-L1.  Pins the oracle restatement the
+    round-2 training path will be checked against; inputs are regenerated from the seed (checksum stored)."""
+    g = golden("losses_cases")
+    T_, chunks, _, _ = synth.LOSS_CASES[name]
+    cfg = synth.make_cfg(T=T_, max_iter=1, NUM_CHUNKS={1: chunks}, image_size=(112, 112))
+    _, _, feat, tb, tg = synth.make_loss_case(name, cfg.num_classes)
+    assert abs(float(feat.double().sum()) - float(g[name + "_feat_checksum"][0])) < 1e-6   # same seeded inputs
+    with torch.no_grad():
+        prob, loc, first, last, logits = om.two_branch(feat, synth.head_state_dict(100, cfg), cfg.T, None, cfg.fc_dim,
+                                                       cfg.pool_size, return_logits=True)
+        lc, ll, ln = om.two_branch_losses(logits, loc, first, last, tb, tg, cfg.T)
+    assert np.allclose(prob.numpy(), g[name + "_prob"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(loc.numpy(), g[name + "_loc"], rtol=1e-4, atol=1e-5)
+    assert lc.shape == tuple(g[name + "_loss_cls"].shape)
+    assert np.allclose(lc.numpy(), g[name + "_loss_cls"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(ll.numpy(), g[name + "_loss_loc"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(ln.numpy(), g[name + "_loss_nb"], rtol=1e-4, atol=1e-6)
+    if name == "nomask":   # no positive sample: the three losses are the scalar 0 (two_branch.py:278-280)
+        assert lc.numel() == 1 and float(lc) == 0.0 and float(ll) == 0.0 and float(ln) == 0.0
