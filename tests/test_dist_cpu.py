@@ -44,3 +44,22 @@ def test_clip_parallel_gather_two_ranks(tmp_path):
         exp = float(rank) + synth.make_clips(2, 4, 8, 8, seed=1234 + rank).mean()
         assert torch.allclose(r["gather"][rank], torch.full((6, 10), float(exp)))
     assert float(r["ms"]) == 11.0
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """`bench.py --impl reference` launched the way the driver launches N > 1 (torchrun, one process per GPU):
+    rank 0 alone runs the reference arithmetic on the host cores and prints ONE JSON line, the other ranks exit 0."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["unit"] == "clips/s"
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["e2e"]["h2d_bytes_per_step"] == 0
