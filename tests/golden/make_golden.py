@@ -196,7 +196,38 @@ def gen_losses():
     np.savez_compressed(os.path.join(OUT, "losses_cases.npz"), **out)
 
 
+def gen_head_grads():
+    """Gradients of the head's training objective (train.py:323-347, train_step.sh:43-44: lambda_reg 5,
+    lambda_neighbor 1) in the reference, eval-mode dropout so that the result is deterministic: the checker the
+    round-2 dgrad / wgrad kernels will be held to.  Stores per-parameter gradient norms and leading values."""
+    out = {}
+    name = "c1"
+    T_, chunks, _, _ = synth.LOSS_CASES[name]
+    cfg = synth.make_cfg(T=T_, max_iter=1, NUM_CHUNKS={1: chunks}, image_size=(112, 112))
+    net = quiet(R.models.TwoBranchNet, cfg)
+    net.load_state_dict(synth.head_state_dict(100, cfg), strict=True)
+    net.eval(); net.set_device("cpu")
+    for p_ in net.parameters():
+        p_.requires_grad_(True)
+    _, _, feat, tubes, tg = synth.make_loss_case(name, cfg.num_classes)
+    feat = feat.clone().requires_grad_(True)
+    prob, loc, first, last, lc, ll, ln = net(feat, None, tubes=tubes, targets=tg)
+    loss = lc.mean() + ll.mean() * 5.0 + ln.mean() * 1.0
+    loss.backward()
+    out["loss"] = loss.detach().numpy().reshape(1)
+    out["feat_grad_norm"] = feat.grad.double().norm().numpy().reshape(1)
+    out["feat_grad_head"] = feat.grad.reshape(-1)[:16].numpy().copy()
+    for k, p_ in net.named_parameters():
+        if p_.grad is None:
+            continue
+        out["gn:" + k] = p_.grad.double().norm().numpy().reshape(1)
+        out["gh:" + k] = p_.grad.reshape(-1)[:8].numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "head_grads.npz"), **out)
+    print("head grads:", float(loss), len([k for k in out if k.startswith("gn:")]), "parameters")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["nms", "roi_align", "tubes", "pipelines", "losses"]
+    which = sys.argv[1:] or ["nms", "roi_align", "tubes", "pipelines", "losses", "head_grads"]
     for w_ in which:
-        {"nms": gen_nms, "roi_align": gen_roi_align, "tubes": gen_tubes, "pipelines": gen_pipelines, "losses": gen_losses}[w_]()
+        {"nms": gen_nms, "roi_align": gen_roi_align, "tubes": gen_tubes, "pipelines": gen_pipelines, "losses": gen_losses,
+         "head_grads": gen_head_grads}[w_]()

@@ -148,3 +148,34 @@ def test_head_losses_oracle_matches_reference(golden, name):
     assert np.allclose(ln.numpy(), g[name + "_loss_nb"], rtol=1e-4, atol=1e-6)
     if name == "nomask":   # no positive sample: the three losses are the scalar 0 (two_branch.py:278-280)
         assert lc.numel() == 1 and float(lc) == 0.0 and float(ll) == 0.0 and float(ln) == 0.0
+
+
+def test_head_gradients_oracle_matches_reference(golden):
+    """Backward of the head's training objective (train.py:323-347 with train_step.sh's lambdas) through the oracle's
+    functional model equals the reference's autograd result: per-parameter gradient norms and leading values.
+    This is the checker for the round-2 dgrad / wgrad kernels."""
+    g = golden("head_grads")
+    name = "c1"
+    T_, chunks, _, _ = synth.LOSS_CASES[name]
+    cfg = synth.make_cfg(T=T_, max_iter=1, NUM_CHUNKS={1: chunks}, image_size=(112, 112))
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running_" not in k)
+          for k, v in synth.head_state_dict(100, cfg).items()}
+    _, _, feat, tb, tg = synth.make_loss_case(name, cfg.num_classes)
+    feat = feat.clone().requires_grad_(True)
+    prob, loc, first, last, logits = om.two_branch(feat, sd, cfg.T, None, cfg.fc_dim, cfg.pool_size, return_logits=True)
+    lc, ll, ln = om.two_branch_losses(logits, loc, first, last, tb, tg, cfg.T)
+    loss = lc.mean() + ll.mean() * 5.0 + ln.mean() * 1.0
+    loss.backward()
+    assert np.allclose(loss.detach().numpy(), g["loss"], rtol=1e-5)
+    assert np.allclose(feat.grad.double().norm().numpy(), g["feat_grad_norm"], rtol=1e-4)
+    assert np.allclose(feat.grad.reshape(-1)[:16].numpy(), g["feat_grad_head"], rtol=1e-3, atol=1e-7)
+    checked = 0
+    for k in g.files:
+        if not k.startswith("gn:"):
+            continue
+        p = sd[k[3:]]
+        assert p.grad is not None, k
+        assert np.allclose(p.grad.double().norm().numpy(), g[k], rtol=1e-4, atol=1e-9), k
+        assert np.allclose(p.grad.reshape(-1)[:8].numpy(), g["gh:" + k[3:]], rtol=1e-3, atol=1e-7), k
+        checked += 1
+    assert checked >= 50   # every trainable tensor of the head (BatchNorm statistics excluded)
