@@ -226,8 +226,33 @@ def gen_head_grads():
     print("head grads:", float(loss), len([k for k in out if k.startswith("gn:")]), "parameters")
 
 
+def gen_trunk_grads():
+    """Backward of the I3D trunk (BatchNorm in eval, affine frozen as build_base_i3d does, networks.py:136-142) for
+    a seeded clip and a seeded linear functional of conv_feat: per-parameter gradient norms -- the checker for the
+    round-2 Unit3D dgrad / wgrad kernels."""
+    cfg = synth.make_cfg(T=2, max_iter=1, NUM_CHUNKS={1: 1}, image_size=(64, 64))
+    net = quiet(R.models.BaseNet, cfg)
+    net.load_state_dict(synth.base_net_state_dict()); net.eval()
+    x = synth.make_clips(1, 8, 64, 64, seed=4321).requires_grad_(True)
+    cf = net(x)
+    proj = torch.randn(cf.shape, generator=torch.Generator().manual_seed(99))
+    loss = (cf * proj).sum() / cf.numel()
+    loss.backward()
+    out = {"loss": loss.detach().numpy().reshape(1), "x_grad_norm": x.grad.double().norm().numpy().reshape(1),
+           "x_grad_head": x.grad.reshape(-1)[:16].numpy().copy()}
+    n = 0
+    for k, p_ in net.named_parameters():
+        if p_.grad is None:
+            continue
+        out["gn:" + k] = p_.grad.double().norm().numpy().reshape(1)
+        out["gh:" + k] = p_.grad.reshape(-1)[:8].numpy().copy()
+        n += 1
+    np.savez_compressed(os.path.join(OUT, "trunk_grads.npz"), **out)
+    print("trunk grads:", float(loss), n, "parameters with gradients")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["nms", "roi_align", "tubes", "pipelines", "losses", "head_grads"]
+    which = sys.argv[1:] or ["nms", "roi_align", "tubes", "pipelines", "losses", "head_grads", "trunk_grads"]
     for w_ in which:
         {"nms": gen_nms, "roi_align": gen_roi_align, "tubes": gen_tubes, "pipelines": gen_pipelines, "losses": gen_losses,
-         "head_grads": gen_head_grads}[w_]()
+         "head_grads": gen_head_grads, "trunk_grads": gen_trunk_grads}[w_]()

@@ -179,3 +179,27 @@ def test_head_gradients_oracle_matches_reference(golden):
         assert np.allclose(p.grad.reshape(-1)[:8].numpy(), g["gh:" + k[3:]], rtol=1e-3, atol=1e-7), k
         checked += 1
     assert checked >= 50   # every trainable tensor of the head (BatchNorm statistics excluded)
+
+
+def test_trunk_gradients_oracle_matches_reference(golden):
+    """Backward of the I3D trunk (45 Unit3D convolutions, BatchNorm eval + frozen affine) through the oracle's
+    functional model equals the reference's autograd result.  Checker for the round-2 conv dgrad / wgrad kernels."""
+    g = golden("trunk_grads")
+    sd = {k: v.clone().requires_grad_(k.endswith("conv3d.weight")) for k, v in synth.base_net_state_dict().items()}
+    x = synth.make_clips(1, 8, 64, 64, seed=4321).requires_grad_(True)
+    cf = om.base_net(x, sd)
+    proj = torch.randn(cf.shape, generator=torch.Generator().manual_seed(99))
+    loss = (cf * proj).sum() / cf.numel()
+    loss.backward()
+    assert np.allclose(loss.detach().numpy(), g["loss"], rtol=1e-4, atol=1e-8)
+    assert np.allclose(x.grad.double().norm().numpy(), g["x_grad_norm"], rtol=1e-3)
+    checked = 0
+    for k in g.files:
+        if not k.startswith("gn:"):
+            continue
+        p = sd[k[3:]]
+        assert p.grad is not None, k
+        assert np.allclose(p.grad.double().norm().numpy(), g[k], rtol=1e-3, atol=1e-10), k
+        assert np.allclose(p.grad.reshape(-1)[:8].numpy(), g["gh:" + k[3:]], rtol=2e-3, atol=1e-8), k
+        checked += 1
+    assert checked == 45   # one weight per Unit3D of the trunk (i3dpt.py:184-226); BN affine is frozen
