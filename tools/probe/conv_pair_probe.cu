@@ -28,6 +28,10 @@ __device__ __forceinline__ void mbar_expect(uint64_t* b, uint32_t n) { asm volat
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t ph) {
   asm volatile("{\n\t.reg .pred p;\n\tWP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra.uni DP;\n\tbra.uni WP;\n\tDP:\n\t}" ::"r"(smem_u32(b)), "r"(ph) : "memory");
 }
+// wait with cluster-scope acquire: the arrivals come from both CTAs of the pair
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t ph) {
+  asm volatile("{\n\t.reg .pred p;\n\tWC:\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t@p bra.uni DC;\n\tbra.uni WC;\n\tDC:\n\t}" ::"r"(smem_u32(b)), "r"(ph) : "memory");
+}
 // arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* b, uint32_t cta) {
   uint32_t remote;
@@ -131,7 +135,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int it = 0;
       for (int tile = pair; tile < total; tile += npairs, ++it) {
         const int buf = it & 1;
-        mbar_wait(&tempty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this set
+        mbar_wait_cluster(&tempty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this set
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tmem_base + (uint32_t)buf * ncols;
         for (int kb = 0; kb < num_kb; ++kb) {
