@@ -60,6 +60,24 @@ int step_nms_f32(const float* boxes /*[n,4]*/, const float* scores /*[n]*/, int 
  * dropped before NMS (test.py:183 confidence threshold; pass -INF to disable). */
 int step_nms_segmented_f32(const float* boxes, const float* scores, const int* seg_offsets, int n_seg,
                            float thr, int ge, float min_score, uint8_t* keep_mask, step_stream_t stream);
+/* Rows one segment may hold (shared-memory resident problem); a longer segment traps instead of overrunning. */
+int step_nms_segmented_max_rows(void);
+
+/* Detection post-processing of the reference drivers (test.py:156-218, demo.py:121-198) in two launches, no host
+ * round trip: for every (clip, class) keep the tubes whose class score > conf_thresh (scores.gt, test.py:183), clamp
+ * their box with valid_tubes(valid_w, valid_h) (the drivers use its 400x400 defaults, test.py:191), greedy NMS with the
+ * cpu/nms_cpu.cpp predicate, divide by (norm_w, norm_h) (test.py:197-198); then per clip either all survivors in file
+ * order (class, tube) when topk <= 0, or the topk best in the order of the tuple sort of test.py:205-208.
+ *   prob [n_rows, prob_ld >= ncls]  class scores of the centre frame;  loc: centre-frame box of row r at loc + r*loc_ld
+ *   clip_offsets [n_clips+1] (device int32): rows of clip b = [clip_offsets[b], clip_offsets[b+1]), at most
+ *   step_nms_segmented_max_rows() of them (max_per_clip is the caller's host-side bound, checked here).
+ * Candidate arrays (index clip_start*ncls + class*n_clip + tube): keep [n_rows*ncls] u8, score [n_rows*ncls],
+ * box [n_rows*ncls, 4] normalised.  Compact result: det [n_clips, cap, 8] = {x1, y1, x2, y2, score, class, tube, 0},
+ * det_count [n_clips] (int32, <= cap). */
+int step_detect_f32(const float* prob, int prob_ld, const float* loc, int loc_ld, const int* clip_offsets,
+                    int n_clips, int n_rows, int max_per_clip, int ncls, float conf_thresh, float nms_thresh,
+                    int ge, float valid_w, float valid_h, float norm_w, float norm_h, int topk, int cap,
+                    uint8_t* keep, float* score, float* box, float* det, int* det_count, step_stream_t stream);
 
 /* ------------------------------------------------------------------ ROI ops -------------- */
 /* Reference layout (NCHW fp32 in, [R,C,ph,pw] fp32 out), arithmetic order of the reference. */

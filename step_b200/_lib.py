@@ -41,6 +41,8 @@ def _declare(lib):
         "step_nms_workspace_bytes": ([I], c_size_t),
         "step_nms_f32": ([P, P, I, Fl, I, P, P, P, c_size_t, S], c_int),
         "step_nms_segmented_f32": ([P, P, P, I, Fl, I, Fl, P, S], c_int),
+        "step_nms_segmented_max_rows": ([], c_int),
+        "step_detect_f32": ([P, I, P, I, P, I, I, I, I, Fl, Fl, I, Fl, Fl, Fl, Fl, I, I, P, P, P, P, P, S], c_int),
         "step_roi_align_fwd_nchw_f32": ([P, I, I, I, I, P, I, Fl, I, I, I, P, S], c_int),
         "step_roi_align_bwd_nchw_f32": ([P, P, I, Fl, I, I, I, I, I, I, I, P, S], c_int),
         "step_roi_pool_fwd_nchw_f32": ([P, I, I, I, I, P, I, Fl, I, I, P, P, S], c_int),
@@ -94,8 +96,25 @@ def check(rc):
         raise RuntimeError("step_b200 [%d]: %s" % (rc, lib().step_last_error().decode("utf-8", "replace")))
 
 
-def stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(device=None):
+    """The launch stream: torch's current stream of `device` (default: the current device).  Callers working on
+    tensors of another GPU wrap their launches in `torch.cuda.device(dev)` (kernels must run on the device that owns
+    their pointers; test.py:85-87 places det_net i on cuda:(i+1) % gpu_count)."""
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def same_device(*tensors):
+    """All CUDA tensors of one launch must live on one device; returns it."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        need_cuda(t)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("step_b200: tensors of one launch on different devices (%s vs %s)" % (dev, t.device))
+    return dev
 
 
 def ptr(t):

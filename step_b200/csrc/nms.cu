@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(256) nms_segmented_kernel(const float* __restr
   __shared__ int m_s;
   const int beg = seg_offsets[blockIdx.x], n = seg_offsets[blockIdx.x + 1] - beg;
   if (n <= 0) return;
+  if (n > kSegMax) __trap();   // callers check step_nms_segmented_max_rows(); never overrun shared memory
   if (threadIdx.x == 0) m_s = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) ss[i] = scores[beg + i];
   __syncthreads();
@@ -200,6 +201,126 @@ __global__ void __launch_bounds__(256) nms_segmented_kernel(const float* __restr
     __syncthreads();
   }
   for (int i = threadIdx.x; i < m; i += blockDim.x) keep_mask[beg + sorig[i]] = sup[i] ? 0 : 1;
+}
+
+
+// ---- detection post-processing (test.py:156-218 / demo.py:121-198) -----------------------------------------------
+// The reference drivers loop on the host over clips x classes: scores.gt(conf) -> valid_tubes(default 400x400) -> nms
+// -> normalise -> (optional) the topk best scores of the clip.  Two launches do the same on the device:
+//   detect_nms_kernel     one CTA per (clip, class): gathers the centre-frame boxes and the class column straight from
+//                         pred_loc / pred_prob (no gather tensors), rank-sorts the candidates above the threshold,
+//                         greedy NMS in shared memory (bit-exact predicate above), writes keep / score / normalised box
+//                         at candidate index  clip_start * ncls + c * n_clip + j.
+//   detect_select_kernel  one CTA per clip: orders the kept candidates as the reference does -- file order (class, tube)
+//                         when topk <= 0, else the tuple sort of test.py:205-208, (score, class, j) descending, cut at
+//                         topk -- and writes them compactly: det[clip][rank] = {x1, y1, x2, y2, score, class, tube, 0}.
+__device__ __forceinline__ float4 valid_box(float4 b, float width, float height) {
+  // tube_utils.py:72-88 (same arithmetic as tubes.cu::valid_one)
+  b.x = fmaxf(0.0f, b.x); b.y = fmaxf(0.0f, b.y);
+  b.z = fminf(width, b.z); b.w = fminf(height, b.w);
+  if (!(b.x < __fsub_rn(b.z, 2.0f) && b.y < __fsub_rn(b.w, 2.0f))) { b.x = 0.0f; b.y = 0.0f; b.z = width; b.w = height; }
+  return b;
+}
+
+__global__ void __launch_bounds__(128) detect_nms_kernel(const float* __restrict__ prob, int prob_ld,
+                                                         const float* __restrict__ loc, int loc_ld,
+                                                         const int* __restrict__ clip_offsets, int ncls, float conf,
+                                                         float thr, int ge, float vw, float vh, float nw, float nh,
+                                                         uint8_t* __restrict__ keep, float* __restrict__ score_out,
+                                                         float4* __restrict__ box_out) {
+  __shared__ float4 sb[kSegMax];
+  __shared__ float sa[kSegMax];
+  __shared__ float ss[kSegMax];
+  __shared__ short sorig[kSegMax];
+  __shared__ uint8_t sup[kSegMax];
+  __shared__ int m_s;
+  const int clip = blockIdx.x / ncls, c = blockIdx.x - clip * ncls;
+  const int beg = clip_offsets[clip], n = clip_offsets[clip + 1] - beg;
+  if (n <= 0) return;
+  if (n > kSegMax) __trap();   // the host checks this bound (step_detect_f32: max_per_clip); never overrun shared memory
+  const size_t cand0 = (size_t)beg * ncls + (size_t)c * n;
+  if (threadIdx.x == 0) m_s = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) ss[i] = prob[(size_t)(beg + i) * prob_ld + c];
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float si = ss[i];
+    const float* lp = loc + (size_t)(beg + i) * loc_ld;
+    const float4 b = valid_box(make_float4(lp[0], lp[1], lp[2], lp[3]), vw, vh);   // test.py:191
+    score_out[cand0 + i] = si;
+    box_out[cand0 + i] = make_float4(__fdiv_rn(b.x, nw), __fdiv_rn(b.y, nh), __fdiv_rn(b.z, nw), __fdiv_rn(b.w, nh));  // test.py:197-198
+    if (si > conf) {                                                                // test.py:183 scores.gt(conf)
+      int rank = 0;
+      for (int t = 0; t < n; ++t) {
+        const float st = ss[t];
+        rank += (st > conf) && ((st > si) || (st == si && t < i));
+      }
+      sb[rank] = b;
+      sa[rank] = box_area(b);
+      sorig[rank] = (short)i;
+      atomicAdd(&m_s, 1);
+    } else {
+      keep[cand0 + i] = 0;
+    }
+  }
+  __syncthreads();
+  const int m = m_s;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) sup[i] = 0;
+  __syncthreads();
+  for (int i = 0; i < m; ++i) {
+    if (!sup[i]) {
+      const float4 a = sb[i];
+      const float aa = sa[i];
+      for (int j = i + 1 + threadIdx.x; j < m; j += blockDim.x)
+        if (!sup[j] && suppresses(a, aa, sb[j], sa[j], thr, ge)) sup[j] = 1;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < m; i += blockDim.x) keep[cand0 + sorig[i]] = sup[i] ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(256) detect_select_kernel(const uint8_t* __restrict__ keep,
+                                                            const float* __restrict__ score, const float4* __restrict__ box,
+                                                            const int* __restrict__ clip_offsets, int ncls, int topk,
+                                                            int cap, float* __restrict__ det, int* __restrict__ det_count) {
+  const int clip = blockIdx.x;
+  const int beg = clip_offsets[clip], n = clip_offsets[clip + 1] - beg;
+  const int cands = n * ncls;
+  const size_t cand0 = (size_t)beg * ncls;
+  __shared__ int total_s;
+  if (threadIdx.x == 0) total_s = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < cands; i += blockDim.x) {
+    if (!keep[cand0 + i]) continue;
+    ++local;
+    const float si = score[cand0 + i];
+    int rank = 0;
+    if (topk > 0) {
+      // (s, class, j) descending; inside a class j grows with the tube index, and the candidate index is
+      // class * n + tube, so "greater (class, j)" == "greater candidate index"
+      for (int t = 0; t < cands; ++t) {
+        if (!keep[cand0 + t]) continue;
+        const float st = score[cand0 + t];
+        rank += (st > si) || (st == si && t > i);
+      }
+      if (rank >= topk) continue;
+    } else {
+      for (int t = 0; t < i; ++t) rank += keep[cand0 + t] ? 1 : 0;
+    }
+    if (rank < cap) {
+      const float4 b = box[cand0 + i];
+      float* o = det + ((size_t)clip * cap + rank) * 8;
+      const int c = i / n;
+      o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = si; o[5] = (float)c; o[6] = (float)(i - c * n); o[7] = 0.0f;
+    }
+  }
+  atomicAdd(&total_s, local);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int k = total_s;
+    if (topk > 0 && k > topk) k = topk;
+    det_count[clip] = k < cap ? k : cap;
+  }
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -261,5 +382,28 @@ extern "C" int step_nms_segmented_f32(const float* boxes, const float* scores, c
   STEP_CHECK_ARG(((uintptr_t)boxes & 15) == 0, "step_nms_segmented_f32: boxes must be 16-byte aligned");
   nms_segmented_kernel<<<n_seg, 256, 0, cu(stream)>>>(boxes, scores, seg_offsets, thr, ge, min_score, keep_mask);
   STEP_LAUNCH_CHECK("nms_segmented_kernel");
+  return 0;
+}
+
+extern "C" int step_nms_segmented_max_rows(void) { return kSegMax; }
+
+extern "C" int step_detect_f32(const float* prob, int prob_ld, const float* loc, int loc_ld, const int* clip_offsets,
+                               int n_clips, int n_rows, int max_per_clip, int ncls, float conf_thresh, float nms_thresh,
+                               int ge, float valid_w, float valid_h, float norm_w, float norm_h, int topk, int cap,
+                               uint8_t* keep, float* score, float* box, float* det, int* det_count,
+                               step_stream_t stream) {
+  STEP_CHECK_ARG(n_clips >= 0 && n_rows >= 0 && ncls > 0, "step_detect_f32: bad sizes");
+  if (n_clips == 0) return 0;
+  STEP_CHECK_ARG(max_per_clip <= kSegMax, "step_detect_f32: %d tubes in one clip (max %d per (clip, class) problem)",
+                 max_per_clip, kSegMax);
+  STEP_CHECK_ARG(prob && loc && clip_offsets && keep && score && box && det && det_count, "step_detect_f32: null pointer");
+  STEP_CHECK_ARG(prob_ld >= ncls && loc_ld >= 4 && cap > 0, "step_detect_f32: bad strides / cap");
+  STEP_CHECK_ARG(((uintptr_t)box & 15) == 0, "step_detect_f32: box must be 16-byte aligned");
+  cudaStream_t s = cu(stream);
+  detect_nms_kernel<<<n_clips * ncls, 128, 0, s>>>(prob, prob_ld, loc, loc_ld, clip_offsets, ncls, conf_thresh, nms_thresh,
+                                                   ge, valid_w, valid_h, norm_w, norm_h, keep, score, (float4*)box);
+  STEP_LAUNCH_CHECK("detect_nms_kernel");
+  detect_select_kernel<<<n_clips, 256, 0, s>>>(keep, score, (const float4*)box, clip_offsets, ncls, topk, cap, det, det_count);
+  STEP_LAUNCH_CHECK("detect_select_kernel");
   return 0;
 }

@@ -33,7 +33,9 @@ _side_streams = {}
 
 
 def side_streams(device, n=3):
-    key = (device.type, device.index)
+    # keyed by the CALLER's stream too: a side stream then only ever runs work forked from (and joined back into) one
+    # stream, so a block freed by the caller and re-used on the side stream is ordered behind the caller's consumer
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     st = _side_streams.get(key)
     if st is None or len(st) < n:
         st = [torch.cuda.Stream(device=device) for _ in range(n)]
@@ -117,6 +119,12 @@ def same_pad(k, s):
     return pad // 2, pad - pad // 2
 
 
+def same_out_dims(dims, k, stride):
+    """Output extent of the reference's SAME emulation, i3dpt.py:14-31,95-98: pad max(k - s, 0) in total, then a
+    VALID convolution -> (D + max(k - s, 0) - k) // s + 1 (= floor(D / s) for odd D when k > s, not ceil)."""
+    return tuple((d + max(kk - s, 0) - kk) // s + 1 for d, kk, s in zip(dims, k, stride))
+
+
 def pack_conv_weight(w, code, cin_pad=None):
     """[Cout, Cin, *k] (Conv3d / Conv2d layout) -> [Cout, taps, cin_pad] in the compute dtype."""
     Cout, Cin = w.shape[0], w.shape[1]
@@ -169,7 +177,7 @@ def conv(x, w_packed, scale, shift, out, k, stride=(1, 1, 1), pad_lo=None, relu=
     if pad_lo is None:
         pad_lo = tuple(same_pad(k[i], stride[i])[0] for i in range(3))
     if out_dims is None:
-        out_dims = tuple(-(-d // s) for d, s in zip((x.T, x.H, x.W), stride))
+        out_dims = same_out_dims((x.T, x.H, x.W), k, stride)
     p = L.ConvParams()
     p.dtype = code
     p.N, p.T, p.H, p.W = x.N, x.T, x.H, x.W

@@ -63,7 +63,7 @@ class Unit3Dpy(torch.nn.Module):
             pad_lo, dims = None, None
         w, scale, shift = self.packed(x.code)
         if out is None:
-            od = dims or tuple(-(-d // s) for d, s in zip((x.T, x.H, x.W), self.stride))
+            od = dims or E.same_out_dims((x.T, x.H, x.W), self.kernel_size, self.stride)
             out = Act.empty(x.N, od[0], od[1], od[2], self.conv3d.out_channels, x.code, x.device)
         return E.conv(x, w, scale, shift, out, self.kernel_size, self.stride, pad_lo, relu, residual, out_dims=dims)
 

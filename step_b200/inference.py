@@ -45,31 +45,44 @@ def inference_device(args, feat, ctx_all, nets, exec_iter, flat, clip_of_tube, t
     history, steps = [], []
     width, height = float(args.image_size[0]), float(args.image_size[1])
     decode_nb = args.temporal_mode == "predict"
-    for i in range(1, exec_iter + 1):
-        chunks = args.NUM_CHUNKS[i]
-        T_start = int((args.NUM_CHUNKS[args.max_iter] - chunks) / 2) * args.T
-        T_len = chunks * args.T
-        if flat.shape[1] != T_len:
-            raise RuntimeError("inference: tubes have %d frames but step %d pools %d" % (flat.shape[1], i, T_len))
-        head = nets['det_net%d' % (i - 1)]
-        ps = head.pool_size
-        # ROI pooling straight into [ROI feat | downsample] concat buffer (utils.py:48, two_branch.py:256)
-        cat = Act.empty(R, T_len, ps, ps, 832 + head.fc_dim, code, dev)
-        roi_net.pool_into(feat, flat, cat.frames().slice(0, 832), T_len, T_total, T_start)
-        ctx_mean = None
-        if ctx_all is not None:
-            sl = ctx_all[:, T_start:T_start + T_len].contiguous()
-            ctx_mean = E.mean_mid(sl.data_ptr(), L.F32, B, T_len, 1, sl.shape[2], sl.shape[2], dev)
-        prob, loc, first, last = head.forward_act(cat, ctx_mean, clip_of_tube)
-        ext = _ext_mode(args, i)
-        pred_loc, pf, pl, flat_next = tube_update(flat, loc, first if decode_nb else None,
-                                                  last if decode_nb else None, clip_of_tube, args.T, decode_nb,
-                                                  ext, width, height)
-        pred_prob = prob.view(-1, 1, args.num_classes).expand(-1, T_len, -1)
-        history.append({'pred_prob': pred_prob, 'pred_loc': pred_loc, 'pred_first_loc': pf, 'pred_last_loc': pl,
-                        'tubes_nums': tubes_nums})
-        steps.append((flat_next, prob))
-        flat = flat_next
+    with torch.cuda.device(dev):
+        for i in range(1, exec_iter + 1):
+            chunks = args.NUM_CHUNKS[i]
+            T_start = int((args.NUM_CHUNKS[args.max_iter] - chunks) / 2) * args.T
+            T_len = chunks * args.T
+            if flat.shape[1] != T_len:
+                raise RuntimeError("inference: tubes have %d frames but step %d pools %d" % (flat.shape[1], i, T_len))
+            head = nets['det_net%d' % (i - 1)]
+            ps = head.pool_size
+            # ROI pooling straight into [ROI feat | downsample] concat buffer (utils.py:48, two_branch.py:256)
+            cat = Act.empty(R, T_len, ps, ps, 832 + head.fc_dim, code, dev)
+            roi_net.pool_into(feat, flat, cat.frames().slice(0, 832), T_len, T_total, T_start)
+            ctx_mean = None
+            if ctx_all is not None:
+                sl = ctx_all[:, T_start:T_start + T_len].contiguous()
+                ctx_mean = E.mean_mid(sl.data_ptr(), L.F32, B, T_len, 1, sl.shape[2], sl.shape[2], dev)
+            # test.py:85-87 may have placed this head on another GPU (set_device): pool here, run the head there
+            # (two_branch.py:225-229 moves the pooled feature the same way) and bring the four small results back
+            hdev = torch.device(head.device) if getattr(head, "device", None) not in (None, "cpu") else dev
+            if hdev.type == "cuda" and hdev.index is None:
+                hdev = torch.device("cuda", torch.cuda.current_device())
+            if hdev != dev:
+                cat_h = Act(cat.buf.to(hdev))
+                cm = ctx_mean.to(hdev) if ctx_mean is not None else None
+                with torch.cuda.device(hdev):
+                    outs = head.forward_act(cat_h, cm, clip_of_tube.to(hdev))
+                prob, loc, first, last = (o.to(dev) for o in outs)
+            else:
+                prob, loc, first, last = head.forward_act(cat, ctx_mean, clip_of_tube)
+            ext = _ext_mode(args, i)
+            pred_loc, pf, pl, flat_next = tube_update(flat, loc, first if decode_nb else None,
+                                                      last if decode_nb else None, clip_of_tube, args.T, decode_nb,
+                                                      ext, width, height)
+            pred_prob = prob.view(-1, 1, args.num_classes).expand(-1, T_len, -1)
+            history.append({'pred_prob': pred_prob, 'pred_loc': pred_loc, 'pred_first_loc': pf, 'pred_last_loc': pl,
+                            'tubes_nums': tubes_nums})
+            steps.append((flat_next, prob))
+            flat = flat_next
     return history, steps
 
 
@@ -99,12 +112,13 @@ def inference(args, conv_feat, context_feat, nets, exec_iter, tubes, want_trajec
 
     trajectory = []
     if want_trajectory:  # one synchronisation at the very end instead of B per step
-        for flat_next, prob in steps:
+        for (flat_next, prob), h in zip(steps, history):
             props = flat_next[:, :, 1:].cpu().numpy()
             cls = torch.argmax(prob, dim=-1).cpu()
+            T_len = h['pred_loc'].shape[1]     # utils.py:95: argmax over pred_prob, which has this step's T_len frames
             cur, s = [], 0
             for n in tubes_nums:
-                cur.append((props[s:s + n], cls[s:s + n].view(-1, 1).expand(-1, flat_next.shape[1])))
+                cur.append((props[s:s + n], cls[s:s + n].view(-1, 1).expand(-1, T_len)))
                 s += n
             trajectory.append(cur)
     return history, trajectory

@@ -74,6 +74,7 @@ class ROINet(nn.Module):
 
     def forward(self, conv_feat, tubes):
         """conv_feat [N,T,C,W,H], tubes [num_tubes,T,5] -> [num_tubes*T, C, 7, 7] (networks.py:34-47)."""
+        L.same_device(conv_feat, tubes)
         _, _, C, W, H = conv_feat.size()
         a = act_of(conv_feat)
         if a is not None and self.pool_mode == 'align':
@@ -119,7 +120,9 @@ class BaseNet(nn.Module):
 
     def forward(self, x):
         """x [N,T,C,H,W] fp32 CUDA -> conv_feat [N,T/4,832,H/16,W/16] (logical view)."""
-        return self.forward_act(x).logical()
+        L.need_cuda(x)
+        with torch.cuda.device(x.device):   # nn.DataParallel replicas (test.py:83) run on their own device + stream
+            return self.forward_act(x).logical()
 
     def forward_act(self, x):
         L.need_cuda(x)

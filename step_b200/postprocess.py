@@ -1,75 +1,92 @@
 """Detection post-processing on the device: the per-clip x per-class loop of the reference drivers
-(test.py:156-218, demo.py:121-198 -- B*60*max_iter tiny CPU NMS calls per batch) as ONE segmented launch.
+(test.py:156-218, demo.py:121-198 -- B*60*max_iter tiny CPU NMS calls per batch) as TWO launches of libstep_b200
+(`step_detect_f32`), with no torch arithmetic, no gather tensors and no synchronisation: CUDA-graph capturable.
 
 For every (clip, class): keep tubes whose centre-frame score > conf_thresh, clamp their centre-frame box
 with valid_tubes (the drivers call it with its 400x400 defaults, test.py:191), run greedy NMS
-(cpu/nms_cpu.cpp semantics, bit-exact), normalise by (width, height), then take the top-k scores per clip.
+(cpu/nms_cpu.cpp semantics, bit-exact), normalise by (width, height), then per clip either every survivor in
+file order or the top-k scores in the order of the reference's tuple sort (test.py:205-208).
 """
 import numpy as np
 import torch
 
-from . import tube_utils
-from .roi_layers import nms_segmented
+from . import _lib as L
 
 _plan_cache = {}
 
 
-def _plan(tubes_nums, num_classes, device):
-    key = (tuple(tubes_nums), num_classes, str(device))
+def _plan(tubes_nums, device):
+    """clip_offsets [B+1] int32 on the device (one small H2D per distinct batch shape, cached)."""
+    key = (tuple(int(n) for n in tubes_nums), str(device))
     p = _plan_cache.get(key)
     if p is None:
-        rows, cls, offs, clip = [], [], [0], []
-        start = 0
-        for b, n in enumerate(tubes_nums):
-            for c in range(num_classes):
-                rows.append(np.arange(start, start + n))
-                cls.append(np.full(n, c))
-                clip.append(np.full(n, b))
-                offs.append(offs[-1] + n)
-            start += n
-        cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.int64)
-        p = tuple(torch.from_numpy(a).to(device) for a in
-                  (cat(rows).astype(np.int64), cat(cls).astype(np.int64), np.asarray(offs, np.int32), cat(clip).astype(np.int64)))
+        offs = np.concatenate([[0], np.cumsum(np.asarray(tubes_nums, np.int64))]).astype(np.int32)
+        p = torch.from_numpy(offs).to(device)
         _plan_cache[key] = p
     return p
 
 
+class Detector:
+    """Pre-allocated outputs for one batch shape, so `run` only launches (what StepRunner captures)."""
+
+    def __init__(self, tubes_nums, num_classes, device, conf_thresh, nms_thresh, width, height, topk=0,
+                 valid_size=(400, 400), ge=True):
+        self.nums = [int(n) for n in tubes_nums]
+        self.B, self.R, self.ncls = len(self.nums), int(sum(self.nums)), int(num_classes)
+        self.max_n = max(self.nums) if self.nums else 0
+        if self.max_n > L.lib().step_nms_segmented_max_rows():
+            raise RuntimeError("detect: %d tubes in one clip exceed the %d-row per-(clip, class) NMS problem"
+                               % (self.max_n, L.lib().step_nms_segmented_max_rows()))
+        self.conf, self.thr, self.topk, self.ge = float(conf_thresh), float(nms_thresh), int(topk or 0), bool(ge)
+        self.w, self.h, self.valid = float(width), float(height), (float(valid_size[0]), float(valid_size[1]))
+        self.cap = max(1, min(self.topk, self.max_n * self.ncls) if self.topk > 0 else self.max_n * self.ncls)
+        self.offs = _plan(self.nums, device)
+        n_cand = max(1, self.R * self.ncls)
+        self.keep = torch.zeros((n_cand,), dtype=torch.uint8, device=device)
+        self.score = torch.zeros((n_cand,), dtype=torch.float32, device=device)
+        self.box = torch.zeros((n_cand, 4), dtype=torch.float32, device=device)
+        self.det = torch.zeros((max(self.B, 1), self.cap, 8), dtype=torch.float32, device=device)
+        self.count = torch.zeros((max(self.B, 1),), dtype=torch.int32, device=device)
+
+    def run(self, pred_prob, pred_loc):
+        """pred_prob [R,T,cls] (any strides, e.g. the expand view `inference` returns) | [R,cls]; pred_loc [R,T,4]."""
+        L.need_cuda(pred_prob, pred_loc)
+        prob = pred_prob[:, pred_prob.shape[1] // 2] if pred_prob.dim() == 3 else pred_prob   # test.py:158-159
+        if prob.dtype != torch.float32 or prob.stride(1) != 1:
+            prob = prob.float().contiguous()
+        if pred_loc.dtype != torch.float32 or not pred_loc.is_contiguous():
+            pred_loc = pred_loc.float().contiguous()
+        if prob.shape[0] != self.R or prob.shape[1] != self.ncls:
+            raise RuntimeError("detect: expected %d x %d scores, got %s" % (self.R, self.ncls, tuple(prob.shape)))
+        T = pred_loc.shape[1]
+        mid = pred_loc[:, T // 2]                                                                # test.py:160-161 (view)
+        if self.R and self.B:
+            with torch.cuda.device(prob.device):
+                L.check(L.lib().step_detect_f32(L.ptr(prob), prob.stride(0), L.c_void_p(mid.data_ptr()), pred_loc.stride(0),
+                                                L.ptr(self.offs), self.B, self.R, self.max_n, self.ncls, self.conf, self.thr,
+                                                1 if self.ge else 0, self.valid[0], self.valid[1], self.w, self.h, self.topk,
+                                                self.cap, L.ptr(self.keep), L.ptr(self.score), L.ptr(self.box),
+                                                L.ptr(self.det), L.ptr(self.count), L.stream(prob.device)))
+        return {"det": self.det, "count": self.count, "keep": self.keep, "score": self.score, "box": self.box,
+                "tubes_nums": self.nums}
+
+
 def detect(pred_prob, pred_loc, tubes_nums, conf_thresh, nms_thresh, width, height, topk=0, valid_size=(400, 400)):
     """pred_prob [R,T,cls] | [R,cls], pred_loc [R,T,4] (history[i] of `inference`), all on the device.
-    Returns a dict of device tensors over the R*cls candidate rows (clip-major, class, tube):
-    keep (bool), score, box (normalised x1,y1,x2,y2), tube (row of pred_*), cls, clip -- no synchronisation.
-    With topk > 0, `keep` is further restricted to the k best kept scores of every clip (test.py:205-208)."""
-    prob = pred_prob[:, pred_prob.shape[1] // 2] if pred_prob.dim() == 3 else pred_prob
-    boxes = pred_loc[:, pred_loc.shape[1] // 2].contiguous().clone()
-    tube_utils.valid_tubes(boxes.view(-1, 1, 4), width=valid_size[0], height=valid_size[1])
-    rows, cls, offs, clip = _plan(tubes_nums, prob.shape[1], prob.device)
-    score = prob.float()[rows, cls].contiguous()
-    cand = boxes[rows].contiguous()
-    strictly_greater = float(np.nextafter(np.float32(conf_thresh), np.float32(np.inf)))   # scores.gt(conf_thresh)
-    keep = nms_segmented(cand, score, offs, nms_thresh, min_score=strictly_greater).bool()
-    if topk and topk > 0:
-        masked = torch.where(keep, score, torch.full_like(score, -1.0))
-        ncls = prob.shape[1]
-        start = 0
-        for n in tubes_nums:  # candidate rows of a clip are contiguous: n * ncls of them (views, no sync)
-            cnt = n * ncls
-            if cnt > topk:
-                seg = masked.narrow(0, start, cnt)
-                thr = torch.topk(seg, topk).values[-1]
-                keep.narrow(0, start, cnt).logical_and_(seg >= thr)
-            start += cnt
-    norm = torch.tensor([width, height, width, height], dtype=torch.float32, device=cand.device)
-    return {"keep": keep, "score": score, "box": cand / norm, "tube": rows, "cls": cls, "clip": clip}
+    Returns device tensors, no synchronisation:
+      det [B, cap, 8] = (x1, y1, x2, y2 normalised, score, class, tube-in-clip, 0) and count [B] -- the kept detections
+      of every clip in the reference's order (file order, or best score first when topk > 0);
+      keep / score / box over the R*cls candidate rows (clip-major, class, tube)."""
+    ncls = pred_prob.shape[-1]
+    d = Detector(tubes_nums, ncls, pred_prob.device, conf_thresh, nms_thresh, width, height, topk, valid_size)
+    return d.run(pred_prob, pred_loc)
 
 
-def to_lists(det, n_clips):
-    """Materialise (one D2H) as per-clip lists of (box[4], cls, score), best score first."""
-    k = det["keep"].cpu().numpy()
-    sc, bx = det["score"].cpu().numpy()[k], det["box"].cpu().numpy()[k]
-    cl, cp = det["cls"].cpu().numpy()[k], det["clip"].cpu().numpy()[k]
+def to_lists(det, n_clips=None):
+    """Materialise (one D2H of the compact result) as per-clip lists of (box[4], cls, score), reference order."""
+    cnt = det["count"].cpu().numpy()
+    rows = det["det"].cpu().numpy()
     out = []
-    for b in range(n_clips):
-        m = np.nonzero(cp == b)[0]
-        m = m[np.argsort(-sc[m], kind="stable")]
-        out.append([(bx[i], int(cl[i]), float(sc[i])) for i in m])
+    for b in range(len(det["tubes_nums"]) if n_clips is None else n_clips):
+        out.append([(rows[b, k, :4].copy(), int(rows[b, k, 5]), float(rows[b, k, 4])) for k in range(int(cnt[b]))])
     return out

@@ -13,15 +13,33 @@ from torch.nn.modules.utils import _pair
 
 from . import _lib as L
 
-# One cached workspace per device for the single-problem NMS entry point.
+import functools
+
+# One cached workspace per (device, stream) for the single-problem NMS entry point.
 _nms_ws = {}
 
 
+def _on_device_of(argpos):
+    """Run the wrapped op with the CUDA device of its `argpos`-th argument current, so that allocations and the launch
+    stream (L.stream()) belong to the device that owns the tensors (multi-GPU drivers: test.py:79-95)."""
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*a, **k):
+            t = a[argpos]
+            if torch.is_tensor(t) and t.is_cuda:
+                with torch.cuda.device(t.device):
+                    return fn(*a, **k)
+            return fn(*a, **k)
+        return wrapped
+    return deco
+
+
 def _workspace(device, nbytes):
-    buf = _nms_ws.get(device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)   # two streams must not share scratch memory
+    buf = _nms_ws.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _nms_ws[device] = buf
+        _nms_ws[key] = buf
     return buf
 
 
@@ -66,11 +84,18 @@ def nms(dets, scores, threshold):
 _CUDA_GE = 1
 
 
-def nms_segmented(boxes, scores, seg_offsets, threshold, min_score=float("-inf"), ge=True):
+@_on_device_of(0)
+def nms_segmented(boxes, scores, seg_offsets, threshold, min_score=float("-inf"), ge=True, max_seg_rows=None):
     """Batched form of the per-clip x per-class loop of test.py:178-201: rows
-    [seg_offsets[s], seg_offsets[s+1]) are independent NMS problems (<= 1024 rows each).
-    Returns a uint8 keep mask over all rows; stays on device, no synchronisation."""
-    L.need_cuda(boxes, scores, seg_offsets)
+    [seg_offsets[s], seg_offsets[s+1]) are independent NMS problems (<= 1024 rows each: pass the longest segment as
+    `max_seg_rows` when the host knows it, otherwise it is read back once).
+    Returns a uint8 keep mask over all rows; stays on device."""
+    L.same_device(boxes, scores, seg_offsets)
+    if max_seg_rows is None:   # the host knows the segment lengths in every caller of ours; a stray caller pays one sync
+        max_seg_rows = int((seg_offsets[1:] - seg_offsets[:-1]).max().item()) if seg_offsets.numel() > 1 else 0
+    if max_seg_rows > L.lib().step_nms_segmented_max_rows():
+        raise RuntimeError("nms_segmented: a segment of %d rows exceeds the %d-row shared-memory problem size"
+                           % (max_seg_rows, L.lib().step_nms_segmented_max_rows()))
     boxes = boxes.contiguous().float()
     scores = scores.contiguous().float()
     seg_offsets = seg_offsets.contiguous().to(torch.int32)
@@ -91,13 +116,14 @@ class _ROIAlign(Function):
     """roi_layers/roi_align.py:45-76"""
 
     @staticmethod
+    @_on_device_of(1)
     def forward(ctx, input, roi, output_size, spatial_scale, sampling_ratio):
         ctx.save_for_backward(roi)
         ctx.output_size = _pair(output_size)
         ctx.spatial_scale = spatial_scale
         ctx.sampling_ratio = sampling_ratio
         ctx.input_shape = input.size()
-        L.need_cuda(input, roi)  # "no CPU fallback": ROIAlign.h:46 path is not reproduced
+        L.same_device(input, roi)  # "no CPU fallback": ROIAlign.h:46 path is not reproduced
         ph, pw = ctx.output_size
         K, C, H, W = input.shape
         rois = roi.detach().to(torch.float32).contiguous()
@@ -120,6 +146,7 @@ class _ROIAlign(Function):
 
     @staticmethod
     @once_differentiable
+    @_on_device_of(1)
     def backward(ctx, grad_output):
         rois, = ctx.saved_tensors
         ph, pw = ctx.output_size
@@ -157,6 +184,7 @@ class _ROIPool(Function):
     """roi_layers/roi_pool.py:45-79"""
 
     @staticmethod
+    @_on_device_of(1)
     def forward(ctx, input, roi, output_size, spatial_scale):
         ctx.output_size = _pair(output_size)
         ctx.spatial_scale = spatial_scale
@@ -176,6 +204,7 @@ class _ROIPool(Function):
 
     @staticmethod
     @once_differentiable
+    @_on_device_of(1)
     def backward(ctx, grad_output):
         rois, argmax = ctx.saved_tensors
         ph, pw = ctx.output_size

@@ -16,10 +16,15 @@ import torch
 from . import _lib as L
 from . import engine as E
 from .inference import inference_device, stage_tubes
+from .postprocess import Detector
 
 
 class StepRunner:
-    def __init__(self, cfg, nets, B, T_in, H, W, tubes, device=None, context=False, use_graph=True, warmup=2):
+    def __init__(self, cfg, nets, B, T_in, H, W, tubes, device=None, context=False, use_graph=True, warmup=2,
+                 detect=None):
+        """detect: None, or dict(conf_thresh, nms_thresh, topk[, steps]) -- the reference drivers' detection
+        post-processing (test.py:156-218: confidence threshold, valid_tubes, per-class NMS, top-k) appended to the
+        captured step for the listed refinement steps (default: the last one); results in `self.detections`."""
         self.cfg, self.nets = cfg, nets
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.context = context and not cfg.no_context
@@ -27,6 +32,12 @@ class StepRunner:
         self.flat, self.clip_of_tube, self.tubes_nums = stage_tubes(tubes, self.device)
         self.graph = None
         self.history = None
+        self.detections = None
+        self.detectors = {}
+        if detect is not None:
+            for i in detect.get("steps", [cfg.max_iter - 1]):
+                self.detectors[i] = Detector(self.tubes_nums, cfg.num_classes, self.device, detect["conf_thresh"],
+                                             detect["nms_thresh"], W, H, topk=detect.get("topk", 0))
         if not use_graph:
             return
         side = torch.cuda.Stream(device=self.device)
@@ -47,6 +58,8 @@ class StepRunner:
             ctx_all = self.nets["context_net"].forward_act(feat) if self.context else None
             hist, _ = inference_device(self.cfg, feat, ctx_all, self.nets, self.cfg.max_iter, self.flat,
                                        self.clip_of_tube, self.tubes_nums)
+            if self.detectors:
+                self.detections = {i: d.run(hist[i]["pred_prob"], hist[i]["pred_loc"]) for i, d in self.detectors.items()}
         return hist
 
     def __call__(self, clips=None):

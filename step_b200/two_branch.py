@@ -138,7 +138,9 @@ class ContextNet(nn.Module):
         self._init_net()
 
     def forward(self, conv_feat):
-        ctx = self.forward_act(to_act(conv_feat, E.dtype_code(self.fp16)))  # [N, T', 1024] fp32
+        L.need_cuda(conv_feat)
+        with torch.cuda.device(conv_feat.device):
+            ctx = self.forward_act(to_act(conv_feat, E.dtype_code(self.fp16)))  # [N, T', 1024] fp32
         return ctx.permute(0, 2, 1).unsqueeze(-1).unsqueeze(-1)
 
     def forward_act(self, a):
@@ -231,20 +233,20 @@ class TwoBranchNet(nn.Module):
             global_feat = global_feat.to(dev)
             if context_feat is not None:
                 context_feat = context_feat.to(dev)
-        L.need_cuda(global_feat)
+        L.same_device(global_feat, context_feat)
         code = E.dtype_code(self.fp16)
         N, T, C, W, H = global_feat.shape
-        # stage [ROI features | downsample output] in one [N*T,7,7,1088] buffer (two_branch.py:256)
-        cat = Act.empty(N, T, W, H, C + self.fc_dim, code, global_feat.device)
-        src = to_act(global_feat, code)
-        cat.buf[..., :C].copy_(src.buf[..., src.coff:src.coff + C])
-        ctx_mean = None
-        if context_feat is not None:
-            L.need_cuda(context_feat)
-            cf = context_feat.detach().float().contiguous().view(N * context_feat.shape[1], T)
-            # mean over T' of [N*1024, T', 1] -> [N, 1024]
-            ctx_mean = E.mean_mid(cf.data_ptr(), L.F32, N * context_feat.shape[1], T, 1, 1, 1, cf.device).view(N, -1)
-        prob, loc, first, last = self.forward_act(cat, ctx_mean, None)
+        with torch.cuda.device(global_feat.device):   # kernels run on the device (and its stream) that owns the tensors
+            # stage [ROI features | downsample output] in one [N*T,7,7,1088] buffer (two_branch.py:256)
+            cat = Act.empty(N, T, W, H, C + self.fc_dim, code, global_feat.device)
+            src = to_act(global_feat, code)
+            cat.buf[..., :C].copy_(src.buf[..., src.coff:src.coff + C])
+            ctx_mean = None
+            if context_feat is not None:
+                cf = context_feat.detach().float().contiguous().view(N * context_feat.shape[1], T)
+                # mean over T' of [N*1024, T', 1] -> [N, 1024]
+                ctx_mean = E.mean_mid(cf.data_ptr(), L.F32, N * context_feat.shape[1], T, 1, 1, 1, cf.device).view(N, -1)
+            prob, loc, first, last = self.forward_act(cat, ctx_mean, None)
         z = torch.tensor(0., device=prob.device)
         return prob, loc, first, last, z.view(-1), z.view(-1), z.view(-1)
 
@@ -306,18 +308,6 @@ class TwoBranchNet(nn.Module):
             hw[k] = w.to(E.torch_dtype(code)).contiguous()
             hw["b12"] = torch.cat([hw[n + "_b"] for n in ("local_reg", "neighbor_reg1", "neighbor_reg2")]).contiguous()
         return hw[k], hw["b12"]
-
-    def _chunk_rows(self, R, T, s0, s1, e0, e1, device):
-        """row indices (into [R*T']) of the first / last chunk frames; cached per shape."""
-        key = (R, T, s0, s1, e0, e1, str(device))
-        c = self.__dict__.get("_rows")
-        if c is None or c[0] != key:
-            base = torch.arange(R, device=device, dtype=torch.int32).view(R, 1) * T
-            f = (base + torch.arange(s0, s1, device=device, dtype=torch.int32).view(1, -1)).reshape(-1).contiguous()
-            l = (base + torch.arange(e0, e1, device=device, dtype=torch.int32).view(1, -1)).reshape(-1).contiguous()
-            self.__dict__["_rows"] = (key, (f, l))
-            c = self.__dict__["_rows"]
-        return c[1]
 
     def _init_net(self):
         self.global_cls.apply(weights_init)

@@ -251,8 +251,159 @@ def gen_trunk_grads():
     print("trunk grads:", float(loss), n, "parameters with gradients")
 
 
+def gen_c4():
+    """BASELINE.json configs[3] (C4) at the measured shape: T_in=32, 224x224, 11 proposals, max_iter=3, spatial mode.
+    The reference runs one clip at a time here (clips are independent units; BatchNorm is in eval mode): clips 0 and 7
+    of the seeded 8-clip bench batch, i.e. the first and the last M tiles of every layer at B=8.  The GPU test runs the
+    whole 8-clip batch, so every dispatch branch the benchmark takes is checked against these rows."""
+    cfg = synth.make_cfg(T=8, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 1}, image_size=(224, 224))
+    nets = build_nets(cfg, cfg.max_iter)
+    xs = synth.make_clips(8, 32, 224, 224)
+    tubes = synth.make_proposals(1, 11, cfg.T, 224, 224)
+    out = {"clips": np.asarray([0, 7]), "B": 8, "T_in": 32, "HW": 224, "N": 11}
+    for c in (0, 7):
+        with torch.no_grad():
+            cf = nets["base_net"](xs[c:c + 1].clone())
+            hist, traj = R.utils.inference(cfg, cf, None, nets, cfg.max_iter, [t.copy() for t in tubes])
+        out["feat_sub_c%d" % c] = cf.numpy()[:, :, ::4].copy()         # every 4th channel, all positions
+        out["feat_absmax_c%d" % c] = np.float32(cf.abs().max().item())
+        out["feat_absmean_c%d" % c] = np.float64(cf.abs().double().mean().item())
+        for i, h in enumerate(hist):
+            out["prob%d_c%d" % (i, c)] = h["pred_prob"][:, 0].numpy().copy()
+            out["loc_valid%d_c%d" % (i, c)] = h["pred_loc"].numpy().copy()
+            out["first%d_c%d" % (i, c)] = h["pred_first_loc"].numpy().copy()
+            out["last%d_c%d" % (i, c)] = h["pred_last_loc"].numpy().copy()
+            out["traj%d_c%d" % (i, c)] = np.concatenate([t[0] for t in traj[i]], 0)
+        print("c4 clip", c, "feat absmax %.3f" % cf.abs().max().item())
+    np.savez_compressed(os.path.join(OUT, "pipe_c4.npz"), **out)
+
+
+def gen_c2():
+    """BASELINE.json configs[1] (C2): I3D trunk only, batch 4, T=32, 224x224.  Reference output for clip 3 of the
+    seeded 4-clip batch (the last M tiles at B=4), every 4th channel."""
+    cfg = synth.make_cfg(T=8, max_iter=1, NUM_CHUNKS={1: 1}, image_size=(224, 224))
+    net = quiet(R.models.BaseNet, cfg)
+    net.load_state_dict(synth.base_net_state_dict()); net.eval()
+    xs = synth.make_clips(4, 32, 224, 224)
+    out = {"B": 4, "T_in": 32, "HW": 224}
+    for c in (0, 3):
+        with torch.no_grad():
+            cf = net(xs[c:c + 1].clone())
+        out["feat_sub_c%d" % c] = cf.numpy()[:, :, ::4].copy()
+        out["feat_absmax_c%d" % c] = np.float32(cf.abs().max().item())
+        out["feat_absmean_c%d" % c] = np.float64(cf.abs().double().mean().item())
+    np.savez_compressed(os.path.join(OUT, "trunk_c2.npz"), **out)
+    print("c2 trunk ok")
+
+
+def _reference_eval_loop_source():
+    """The evaluation loop body of the reference's test.py (the `for i in range(len(history))` block,
+    test.py:156-218), read from the file where it lies and dedented -- executed, never stored."""
+    import textwrap
+    lines = open(os.path.join(refload.REF, "test.py")).read().split("\n")
+    start = next(i for i, l in enumerate(lines) if l.strip() == "for i in range(len(history)):")
+    end = next(i for i in range(start, len(lines)) if lines[i].startswith("    fout.close()"))
+    return textwrap.dedent("\n".join(lines[start:end]))
+
+
+def run_reference_eval_loop(history, n_clips, num_classes, conf_thresh, nms_thresh, topk, width, height):
+    """Executes the reference's own loop body on `history` (CPU tensors) and parses the rows it writes
+    (test.py:211-218 format) back into per-step, per-clip lists of (box[4], class, score) -- in file order."""
+    from types import SimpleNamespace
+    bufs = [io.StringIO() for _ in history]
+    env = {"history": history, "args": SimpleNamespace(num_classes=num_classes, conf_thresh=conf_thresh,
+                                                       nms_thresh=nms_thresh, evaluate_topk=topk, topk=topk),
+           "infos": [{"video_name": "clip%d" % b, "fid": b} for b in range(n_clips)], "fouts": bufs,
+           "label_dict": list(range(num_classes)), "width": width, "height": height, "np": np, "torch": torch,
+           "valid_tubes": R.tube_utils.valid_tubes, "nms": R.roi_layers.nms}
+    exec(compile(_reference_eval_loop_source(), "reference test.py:156-218", "exec"), env)
+    out = []
+    for buf in bufs:
+        per_clip = [[] for _ in range(n_clips)]
+        for row in buf.getvalue().strip().split("\n"):
+            if not row:
+                continue
+            f = row.split(",")
+            per_clip[int(f[1])].append((np.asarray([float(v) for v in f[2:6]], np.float32), int(f[6]), float(f[7])))
+        out.append(per_clip)
+    return out
+
+
+def gen_postprocess():
+    """Detection post-processing (test.py:156-218) by the reference's own code, on (a) a synthetic history with
+    heavy overlaps, ragged / empty clips and scores straddling conf_thresh, (b) the reference's own C4 outputs
+    (pipe_c4.npz, clip 0 and 7 as a 2-clip batch).  The file rows carry 4 significant digits; the raw inputs are
+    stored so the checker re-derives full-precision values and compares sets."""
+    rs = np.random.RandomState(5)
+    out = {}
+
+    def case(name, prob, loc, nums, conf, thr, topk, width, height):
+        T_ = loc.shape[1]
+        hist = [{"pred_prob": T(prob[:, None, :].repeat(T_, 1).copy()), "pred_loc": T(loc.copy()), "tubes_nums": list(nums)}]
+        dets = run_reference_eval_loop(hist, len(nums), prob.shape[1], conf, thr, topk, width, height)[0]
+        out[name + "_prob"], out[name + "_loc"], out[name + "_nums"] = prob, loc, np.asarray(nums)
+        out[name + "_cfg"] = np.asarray([conf, thr, topk, width, height], np.float64)
+        rows = [(b, c, s) + tuple(bx) for b, d in enumerate(dets) for (bx, c, s) in d]
+        out[name + "_rows"] = np.asarray(rows, np.float64).reshape(-1, 7)
+        print("postprocess", name, "detections per clip:", [len(d) for d in dets])
+
+    nums = [6, 0, 9, 3]
+    n = sum(nums)
+    ctr = rs.uniform(40, 180, (n, 1, 2)); wh = rs.uniform(20, 90, (n, 1, 2))
+    jit = rs.uniform(-6, 6, (n, 4, 4))
+    loc = (np.concatenate([ctr - wh / 2, ctr + wh / 2], 2) + jit).astype(np.float32)
+    loc[2] = loc[3] + 1.0          # near-duplicates -> suppressed
+    loc[7, :, 2] = loc[7, :, 0] + 1.0   # degenerate -> valid_tubes replaces it by the 400x400 default box
+    prob = rs.uniform(0, 1, (n, 12)).astype(np.float32) ** 3
+    prob[:, 5] = 0.0
+    prob[4, 3] = np.float32(0.2)   # == conf_thresh: not strictly greater -> dropped
+    case("synth", prob, loc, nums, 0.2, 0.4, 0, 224, 224)
+    case("synth_topk", prob, loc, nums, 0.05, 0.5, 5, 224, 224)
+    g = np.load(os.path.join(OUT, "pipe_c4.npz"))
+    prob = np.concatenate([g["prob2_c0"], g["prob2_c7"]], 0)
+    loc = np.concatenate([g["loc_valid2_c0"], g["loc_valid2_c7"]], 0)
+    # threshold in the middle of the widest score gap of the upper half, so that fp16-vs-fp32 score noise
+    # (<= 5e-3) cannot move a candidate across it: the detection SET is then a meaningful fp16-vs-fp32 comparison
+    sp = np.sort(prob.reshape(-1))
+    band = sp[int(0.50 * sp.size):int(0.95 * sp.size)]
+    k = int(np.argmax(np.diff(band)))
+    conf = float(np.float32(0.5 * (band[k] + band[k + 1])))
+    print("c4 conf_thresh %.5f (gap %.4f)" % (conf, band[k + 1] - band[k]))
+    case("c4", prob, loc, [11, 11], conf, 0.4, 0, 224, 224)
+    np.savez_compressed(os.path.join(OUT, "postprocess_cases.npz"), **out)
+
+
+def gen_roi_cross():
+    """ROIPool forward/backward and ROIAlign backward have no CPU implementation in the reference
+    (csrc/ROIPool.h:47, ROIAlign.h:66 raise on CPU tensors) -> cross-checked against torchvision 0.26's CPU ops,
+    which descend from the same Caffe2 / maskrcnn-benchmark kernels (roi_align(aligned=False) is bit-identical to
+    the reference's forward).  A second independent implementation, not the reference."""
+    import torchvision
+    from torchvision.ops import roi_align as tv_align, roi_pool as tv_pool
+    g = np.load(os.path.join(OUT, "roi_align_cases.npz"))
+    feat, rois = T(g["feat"]), T(g["rois"])
+    out = {"torchvision": np.asarray([int(v) for v in torchvision.__version__.split("+")[0].split(".")[:2]])}
+    gen = torch.Generator().manual_seed(21)
+    for sr in (0, 2):
+        x = feat.clone().requires_grad_(True)
+        y = tv_align(x, rois, (7, 7), 1.0 / 16.0, sr, aligned=False)
+        assert torch.equal(y.detach(), T(g["out_sr%d" % sr])), "torchvision roi_align != reference forward"
+        gy = torch.randn(y.shape, generator=gen)
+        y.backward(gy)
+        out["align_gy_sr%d" % sr] = gy.numpy(); out["align_gx_sr%d" % sr] = x.grad.numpy().copy()
+    x = feat.clone().requires_grad_(True)
+    y = tv_pool(x, rois, (7, 7), 1.0 / 16.0)
+    gy = torch.randn(y.shape, generator=gen)
+    y.backward(gy)
+    out["pool_out"] = y.detach().numpy(); out["pool_gy"] = gy.numpy(); out["pool_gx"] = x.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "roi_cross_cases.npz"), **out)
+    print("roi cross-check cases ok")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["nms", "roi_align", "tubes", "pipelines", "losses", "head_grads", "trunk_grads"]
+    which = sys.argv[1:] or ["nms", "roi_align", "tubes", "pipelines", "losses", "head_grads", "trunk_grads", "c4", "c2",
+                             "postprocess", "roi_cross"]
     for w_ in which:
         {"nms": gen_nms, "roi_align": gen_roi_align, "tubes": gen_tubes, "pipelines": gen_pipelines, "losses": gen_losses,
-         "head_grads": gen_head_grads, "trunk_grads": gen_trunk_grads}[w_]()
+         "head_grads": gen_head_grads, "trunk_grads": gen_trunk_grads, "c4": gen_c4, "c2": gen_c2,
+         "postprocess": gen_postprocess, "roi_cross": gen_roi_cross}[w_]()

@@ -239,3 +239,41 @@ def test_detect_postprocess_matches_reference_loop():
     ref = opp.detections(prob, box, nums, 0.2, 0.4, 224.0, 224.0, topk=10)
     for g, r in zip(got, ref):
         assert [round(s, 6) for _, _, s in g] == [round(s, 6) for _, _, s in r]
+
+
+@pytest.mark.parametrize("name", ["synth", "synth_topk", "c4"])
+def test_detect_matches_reference_loop_rows(golden, name):
+    """step_detect_f32 against the rows the reference's OWN evaluation loop (test.py:156-218, executed from the file where
+    it lies by tests/golden/make_golden.py) wrote: ragged and empty clips, a score equal to conf_thresh, a degenerate
+    box, near-duplicates, top-k.  The rows carry 4 significant digits ('{:.4}'), order included."""
+    from step_b200 import postprocess as pp
+    g = golden("postprocess_cases")
+    conf, thr, topk, width, height = g[name + "_cfg"].tolist()
+    prob, loc, nums = g[name + "_prob"], g[name + "_loc"], g[name + "_nums"].tolist()
+    T = loc.shape[1]
+    det = pp.detect(cu(np.ascontiguousarray(np.tile(prob[:, None, :], (1, T, 1)))), cu(loc), nums, conf, thr, width, height,
+                    topk=int(topk))
+    got = pp.to_lists(det)
+    fmt = lambda v: float("{:.4}".format(float(v)))
+    rows = [(b, c, fmt(s)) + tuple(fmt(v) for v in bx) for b, d in enumerate(got) for (bx, c, s) in d]
+    ref = [(int(r[0]), int(r[1]), fmt(r[2])) + tuple(fmt(v) for v in r[3:7]) for r in g[name + "_rows"]]
+    assert rows == ref            # same detections in the same (file) order
+
+
+def test_roi_pool_and_align_backward_match_torchvision(golden):
+    """The device ROIPool fwd/bwd and ROIAlign bwd against torchvision's CPU ops (the reference has no CPU
+    implementation of them; see tests/golden/make_golden.py::gen_roi_cross)."""
+    from step_b200.roi_layers import roi_align, roi_pool
+    g, a = golden("roi_cross_cases"), golden("roi_align_cases")
+    rois = cu(a["rois"])
+    for sr in (0, 2):
+        x = cu(a["feat"]).requires_grad_(True)
+        y = roi_align(x, rois, (7, 7), 1.0 / 16.0, sr)
+        y.backward(cu(g["align_gy_sr%d" % sr]))
+        ref = g["align_gx_sr%d" % sr]
+        assert np.abs(x.grad.cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    x = cu(a["feat"]).requires_grad_(True)
+    y = roi_pool(x, rois, (7, 7), 1.0 / 16.0)
+    assert np.array_equal(y.detach().cpu().numpy(), g["pool_out"])
+    y.backward(cu(g["pool_gy"]))
+    assert np.abs(x.grad.cpu().numpy() - g["pool_gx"]).max() <= 2e-5 * max(1.0, np.abs(g["pool_gx"]).max())
