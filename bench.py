@@ -32,6 +32,19 @@ sys.path.insert(0, ROOT)
 
 ALG_GFLOP_PER_CLIP = 362.06          # SURVEY.md section 8d / BASELINE.md section 3 (trunk 109.29 + 3 x 84.26)
 WORKLOAD = dict(B=8, T_in=32, HW=224, N=11, max_iter=3)
+# detection post-processing of the reference drivers (test.py:156-218) with the values its scripts ship:
+# config.py:62-63 (conf_thresh 0.01, nms_thresh 0.4), scripts/train_step.sh:50-51 (topk 300)
+DETECT = dict(conf_thresh=0.01, nms_thresh=0.4, topk=300)
+
+
+def csrc_sha():
+    """Hash of the kernel sources, to tie profiles/*.json captures to the build they were taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "step_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def peaks():
@@ -123,20 +136,34 @@ def run_ours(args):
     clips_host = synth.make_clips(B, W["T_in"], W["HW"], W["HW"], seed=1234 + rank).pin_memory()
     clips_dev = clips_host.to(dev)
     tubes = synth.make_proposals(B, W["N"], cfg.T, W["HW"], W["HW"])
-    out_host = {"p": torch.empty((B * W["N"], cfg.num_classes), dtype=torch.float32).pin_memory(),
-                "l": torch.empty((B * W["N"], cfg.T, 4), dtype=torch.float32).pin_memory()}
+    cap = min(DETECT["topk"], W["N"] * cfg.num_classes)
+    # what leaves the GPU per step: the kept detections of every clip {x1,y1,x2,y2,score,class,tube,0} and their count
+    out_host = {"det": torch.empty((B, cap, 8), dtype=torch.float32).pin_memory(),
+                "cnt": torch.empty((B,), dtype=torch.int32).pin_memory()}
     gather = None
     if world > 1:
-        gather = torch.empty((world, B * W["N"], cfg.num_classes + 4), dtype=torch.float32, device=dev)
+        gather = torch.empty((world, B, cap * 8 + 1), dtype=torch.float32, device=dev)
 
-    # eager step first: packs weights, counts the launches of one step
+    # eager step first: packs weights, counts the launches of one step (trunk, 3 refinement steps, detection)
+    eager = step_b200.StepRunner(cfg, nets, B, W["T_in"], W["HW"], W["HW"], tubes, device=dev, use_graph=False, detect=DETECT)
+    eager(clips_dev)
+    torch.cuda.synchronize()
     l_before = _lib.launch_count()
-    with torch.no_grad():
-        cf0 = nets["base_net"](clips_dev)
-        step_b200.inference(cfg, cf0, None, nets, cfg.max_iter, tubes, want_trajectory=False)
+    hist0 = eager(clips_dev)
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - l_before
-    del cf0
+    # rank 0 keeps clip 0's outputs for the same-run parity check against the CPU pass of cpu_baseline
+    gpu_clip0 = None
+    if rank == 0 and not args.skip_cpu:
+        N0 = W["N"]
+        with torch.no_grad():
+            cf0 = nets["base_net"](clips_dev[0:1])
+        d0 = eager.detections[cfg.max_iter - 1]
+        gpu_clip0 = {"feat": cf0.float().cpu(), "prob": [h["pred_prob"][:N0, 0].float().cpu() for h in hist0],
+                     "loc": [h["pred_loc"][:N0].float().cpu() for h in hist0],
+                     "det": d0["det"][0].cpu().numpy().copy(), "cnt": int(d0["count"][0].item())}
+        del cf0
+    del hist0, eager
     # the public fast path: the whole step captured once into a CUDA graph (step_b200/runner.py)
     # args.inflight independent batches are kept in flight on separate streams (double buffering):
     # the H2D copy / small-grid layers of one batch overlap the other batch's kernels.
@@ -147,7 +174,7 @@ def run_ours(args):
         st.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(st):
             runners.append(step_b200.StepRunner(cfg, nets, B, W["T_in"], W["HW"], W["HW"], tubes, device=dev,
-                                                use_graph=not args.no_graph))
+                                                use_graph=not args.no_graph, detect=DETECT))
     torch.cuda.synchronize()
     turn = [0]
 
@@ -157,13 +184,14 @@ def run_ours(args):
         cur = torch.cuda.current_stream(dev)
         streams[i].wait_stream(cur)
         with torch.cuda.stream(streams[i]):
-            last = runners[i](x)[-1]
+            runners[i](x)
+            last = runners[i].detections[cfg.max_iter - 1]     # per-class NMS + top-k ran inside the captured step
         step.last_stream = streams[i]
         if n_run == 1:
             cur.wait_stream(streams[i])
         if gather is not None:  # one NCCL all_gather of the fixed-shape detections per batch
             with torch.cuda.stream(streams[i]):
-                det = torch.cat([last["pred_prob"][:, 0], last["pred_loc"][:, cfg.T // 2]], dim=1).contiguous()
+                det = torch.cat([last["det"].view(B, -1), last["count"].view(B, 1).float()], dim=1).contiguous()
                 dist.all_gather_into_tensor(gather.view(-1, det.shape[1]), det)
         return last
 
@@ -189,7 +217,7 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    host_out = [{"p": torch.empty_like(out_host["p"]).pin_memory(), "l": torch.empty_like(out_host["l"]).pin_memory()}
+    host_out = [{"det": torch.empty_like(out_host["det"]).pin_memory(), "cnt": torch.empty_like(out_host["cnt"]).pin_memory()}
                 for _ in range(n_run)]
     pending = [None] * n_run
 
@@ -201,8 +229,8 @@ def run_ours(args):
             pending[i].synchronize()
         last = step(clips_host)       # StepRunner copies the pinned host batch into its static input
         with torch.cuda.stream(streams[i]):
-            host_out[i]["p"].copy_(last["pred_prob"][:, 0], non_blocking=True)
-            host_out[i]["l"].copy_(last["pred_loc"], non_blocking=True)
+            host_out[i]["det"].copy_(last["det"], non_blocking=True)
+            host_out[i]["cnt"].copy_(last["count"], non_blocking=True)
             pending[i] = streams[i].record_event()
 
     # clocks / throttle reasons are sampled (100 ms period) from the warm-up through both timed regions: the
@@ -270,12 +298,16 @@ def run_ours(args):
             taps = q.KT * q.KH * q.KW
             alg_bytes += 2 * (q.N * q.T * q.H * q.W * q.Cin + q.Cout * taps * q.Cin +
                               q.N * q.OT * q.OH * q.OW * q.Cout * (2 if q.residual else 1))
-        # DRAM bytes the same launches moved in one ncu capture (tools/gpu_profiles.sh -> profiles/r1_conv_traffic.json)
-        traffic = None
-        tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_conv_traffic.json")
+        # DRAM bytes the same launches moved in one ncu capture (tools/gpu_profiles.sh -> profiles/r2_conv_traffic.json).
+        # Only reported when that capture was taken from THIS build (the file is stamped with a hash of the kernel
+        # sources); otherwise null -- a stale number is worse than none.
+        traffic, traffic_src = None, None
+        tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_conv_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_step")
+                tj = json.load(open(tp))
+                if tj.get("csrc_sha") == csrc_sha():
+                    traffic, traffic_src = tj.get("dram_bytes_per_step"), "profiles/r2_conv_traffic.json (ncu, same kernel sources %s)" % tj.get("csrc_sha")
             except Exception:
                 traffic = None
         flops = ALG_GFLOP_PER_CLIP * 1e9 * B
@@ -283,7 +315,7 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": "tcgen05 conv class: conv_umma_kernel + conv_umma_persist_kernel + conv_halo_kernel",
                 "achieved": round(achieved, 2),
                 "peak": pk["tflops"], "peak_source": pk["src"] + " bf16 sustained", "unit": "TFLOP/s",
-                "frac": round(achieved / pk["tflops"], 4), "traffic": traffic, "traffic_unit": "DRAM bytes per step, all conv launches (ncu)",
+                "frac": round(achieved / pk["tflops"], 4), "traffic": traffic, "traffic_unit": "DRAM bytes per step, all conv launches (ncu)", "traffic_source": traffic_src,
                 "algorithmic_bytes_per_step": int(alg_bytes),
                 "launches_per_step": len(rec), "replay": "cuda graph" if replay_fn is not replay else "eager", "ms_per_step_in_kernel": round(ms_conv / max(3, args.steps), 4),
                 "algorithmic_gflop_per_step": round(flops / 1e9, 1)}
@@ -295,7 +327,10 @@ def run_ours(args):
         return
     ms_step = ms / args.steps
     total_clips = world * B * args.steps
-    cpu = None if args.skip_cpu else cpu_baseline(sample_clips=1, passes=2)
+    cpu, parity = None, None
+    if not args.skip_cpu:
+        cpu, ref_out = cpu_baseline(sample_clips=1, passes=2)
+        parity = parity_vs_oracle(gpu_clip0, ref_out, cfg, W)
     line = {
         "metric": "clips/sec (T=32,224x224) STEP max_iter=3", "value": round(total_clips / (ms * 1e-3), 3),
         "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -309,8 +344,8 @@ def run_ours(args):
                    "parallelism": "clip-parallel x%d" % world},
         "e2e": {"value": round(total_clips / (ms_e2e * 1e-3), 3), "unit": "clips/s",
                 "h2d_bytes_per_step": int(clips_host.numel() * 4),
-                "d2h_bytes_per_step": int(out_host["p"].numel() * 4 + out_host["l"].numel() * 4)},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "d2h_bytes_per_step": int(out_host["det"].numel() * 4 + out_host["cnt"].numel() * 4)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
     }
     print(json.dumps(line))
     if world > 1:
@@ -328,7 +363,7 @@ def timed_local(torch, fn, steps):
     return e0.elapsed_time(e1)
 
 
-def oracle_pass(n_clips):
+def oracle_pass(n_clips, want_outputs=False):
     """The reference's own arithmetic (torch-CPU fp32 modules restated in oracle/model.py) on n clips
     of the C4 shape: trunk + 3 refinement steps.  Returns seconds."""
     import torch
@@ -344,25 +379,98 @@ def oracle_pass(n_clips):
     t0 = time.perf_counter()
     with torch.no_grad():
         cf = om.base_net(x, sd)
-        om.inference(cfg, cf, None, heads, cfg.max_iter, tubes)
-    return time.perf_counter() - t0
+        hist, _ = om.inference(cfg, cf, None, heads, cfg.max_iter, tubes)
+    dt = time.perf_counter() - t0
+    return (dt, (cf, hist)) if want_outputs else dt
+
+
+def parity_vs_oracle(gpu, ref_out, cfg, W):
+    """Same-run parity: the GPU outputs of clip 0 of the timed batch (fp16 tensor-core path) against the fp32 CPU pass
+    that cpu_baseline just timed on the same clip (oracle/model.py == the reference's arithmetic, pinned by
+    tests/golden/pipe_c4.npz).  Detection level: the reference's evaluation loop (oracle/postprocess.py, pinned to
+    test.py:156-218) on the CPU outputs vs the device post-processing that ran inside the timed step."""
+    import numpy as np
+    from oracle import postprocess as opp
+    from oracle import tubes as otubes
+    cf, hist = ref_out
+    N = W["N"]
+    ref_feat = cf.numpy()
+    d = np.abs(gpu["feat"].numpy() - ref_feat)
+    out = {"clip": 0, "trunk_rel": round(float(d.max() / np.abs(ref_feat).max()), 6),
+           "trunk_mean_rel": round(float(d.mean() / np.abs(ref_feat).mean()), 6)}
+    s_abs, b_px = 0.0, 0.0
+    for i, h in enumerate(hist):
+        s_abs = max(s_abs, float(np.abs(gpu["prob"][i].numpy() - h["pred_prob"][:N, 0].numpy()).max()))
+        # the CPU run has already clamped pred_loc in place (valid_tubes through the shared numpy view, utils.py:107-121)
+        g_loc = otubes.valid_tubes(gpu["loc"][i].numpy().copy(), W["HW"], W["HW"])
+        r_loc = otubes.valid_tubes(h["pred_loc"][:N].numpy().copy(), W["HW"], W["HW"])
+        b_px = max(b_px, float(np.abs(g_loc - r_loc).max()))
+    out["score_abs"], out["box_px"] = round(s_abs, 6), round(b_px, 4)
+    def det_set(prob, centre_boxes):
+        d = opp.detections(prob, centre_boxes, [N], DETECT["conf_thresh"], DETECT["nms_thresh"], float(W["HW"]), float(W["HW"]),
+                           topk=DETECT["topk"])[0]
+        out_ = set()
+        for bx, c, sc in d:   # the rows carry no tube index: recover it from the score
+            out_.add((int(c), int(np.argmin(np.abs(prob[:, c] - sc)))))
+        return out_
+    last = hist[-1]
+    mid = last["pred_loc"].shape[1] // 2
+    r_prob, r_loc = last["pred_prob"][:N, 0].numpy(), last["pred_loc"][:N].numpy()            # clamped in place by the CPU run
+    g_prob = gpu["prob"][-1].numpy()
+    g_loc_raw = gpu["loc"][-1].numpy()
+    g_loc = otubes.valid_tubes(g_loc_raw.copy(), W["HW"], W["HW"])                               # same clamp as the CPU run
+    ref_set, gpu_set = det_set(r_prob, r_loc[:, mid].copy()), det_set(g_prob, g_loc[:, mid].copy())
+    diff = ref_set ^ gpu_set
+    borderline = sum(1 for (c, t) in diff if abs(float(r_prob[t, c]) - DETECT["conf_thresh"]) < 1e-3)
+    out["nms_keep_equal"] = len(diff) == 0
+    out["detections_ref"], out["detections_gpu"], out["detections_differing"] = len(ref_set), len(gpu_set), len(diff)
+    out["differing_within_1e-3_of_conf_thresh"] = borderline
+    # the device post-processing that ran inside the timed step == the reference loop on the same (GPU) history
+    in_graph = set((int(r[5]), int(r[6])) for r in gpu["det"][:gpu["cnt"]])
+    out["device_detect_equals_reference_loop"] = in_graph == det_set(g_prob, g_loc_raw[:, mid].copy())
+    out["tolerance"] = "fp16 path vs fp32 reference arithmetic: trunk <= 2e-2 of max, scores <= 5e-3, boxes <= 1.5 px (tests/test_gpu_pipeline.py)"
+    out["ok"] = bool(out["trunk_rel"] <= 2e-2 and s_abs <= 5e-3 and b_px <= 1.5)
+    return out
+
+
+_THREADS = None
 
 
 def host_threads():
-    # oneDNN convolutions stop scaling (and collapse on shared hosts) far below 128 threads
-    return min(os.cpu_count() or 1, 32)
+    """The thread count the CPU arm runs best with on this box: every core the process may use,
+    unless 32 threads are faster -- oneDNN convolutions stop scaling, and on shared hosts collapse, well below 128
+    threads.  Both are timed once (this doubles as the warm-up) and the faster one is kept: the CPU arm gets its best
+    configuration, and `cores` reports the count actually used."""
+    global _THREADS
+    if _THREADS is None:
+        import torch
+        allc = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        cands = sorted(set([allc, min(allc, 32)]), reverse=True)
+        best = None
+        for c in cands:
+            torch.set_num_threads(c)
+            oracle_pass(1)                       # oneDNN primitive creation for this thread count
+            t = oracle_pass(1)
+            if best is None or t < best[1]:
+                best = (c, t)
+        _THREADS = best[0]
+        torch.set_num_threads(_THREADS)
+    return _THREADS
 
 
 def cpu_baseline(sample_clips=1, passes=2):
     import torch
     cores = host_threads()
     torch.set_num_threads(cores)
-    oracle_pass(sample_clips)  # warm-up (oneDNN primitive creation)
-    ts = [oracle_pass(sample_clips) for _ in range(passes)]
+    ts, outs = [], None
+    for _ in range(passes):
+        t, outs = oracle_pass(sample_clips, want_outputs=True)
+        ts.append(t)
     best = sorted(ts)[len(ts) // 2]
-    return {"value": round(sample_clips / best, 4), "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": "%d clip(s) of the C4 shape (T=32, 224x224, 11 proposals, 3 steps), fp32 torch-CPU oracle, "
-                      "median of %d passes after 1 warm-up" % (sample_clips, passes)}
+    return ({"value": round(sample_clips / best, 4), "unit": "clips/s", "cores": cores, "kind": "port",
+             "sample": "%d clip(s) of the C4 shape (T=32, 224x224, 11 proposals, 3 steps), fp32 torch-CPU oracle, "
+                       "median of %d passes after warm-up; its outputs are the parity reference of this run"
+                       % (sample_clips, passes)}, outs)
 
 
 def run_reference(args):
@@ -372,10 +480,8 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    cores = host_threads()
+    cores = host_threads()        # times a warm-up pass per candidate thread count and keeps the faster
     torch.set_num_threads(cores)
-    for _ in range(min(args.warmup, 1)):
-        oracle_pass(1)
     steps = min(args.steps, 5)
     t = sum(oracle_pass(1) for _ in range(steps))
     v = round(steps / t, 4)
@@ -393,7 +499,7 @@ def run_reference(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=250, help="timed steps (default: ~1 s of device time)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")

@@ -316,6 +316,53 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+
+// ---- CTA-pair (cta_group::2) protocol helpers; validated by tools/probe/umma_2cta_probe.cu and conv_pair_probe*.cu ----
+// wait with cluster-scope acquire: the arrivals come from both CTAs of the pair
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITC_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAITC_DONE;\n\t"
+      "bra.uni WAITC_LOOP;\n\t"
+      "WAITC_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// TMA loads of a CTA pair: the data lands in the issuing CTA's shared memory, the bytes are signalled on the LEADER's
+// barrier (same offset, CTA-rank bit of the shared::cluster address cleared)
+__device__ __forceinline__ uint32_t leader_bar(uint64_t* bar) { return smem_u32(bar) & 0xFEFFFFFFu; }
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c, int w, int h, int d,
+                                                    int n, uint16_t ow, uint16_t oh, uint16_t od) {
+  asm volatile("cp.async.bulk.tensor.5d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10};"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar(bar)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"(ow), "h"(oh), "h"(od) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// the MMAs issued so far have retired -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 struct HalfOrigin {
   long long m0;            // first output pixel (linear) of this 128-row half (LINEAR / IM2COL)
   int bn, bt0, bh0, bw0;   // BOX origin
@@ -334,7 +381,13 @@ __device__ __forceinline__ HalfOrigin half_origin(const ConvGeom& g, int m_tile)
   return o;
 }
 
-template <int BK, bool kHasRes>
+// kPair: a cluster of two CTAs (the two SMs of a TPC) owns a 256-row x BN tile and runs ONE tcgen05.mma.cta_group::2 per
+// k step: CTA r stages rows [128 r, +128) of A and rows [r BN/2, +BN/2) of B, so an SM pulls in 16 KB + BN/2 * 128 B
+// per k-block (64 B/clk at BN = 256) instead of 16 KB + BN * 128 B (96 B/clk) -- the per-SM operand inbound rate is
+// what bounded the 128-row tiles (1088 -> 1024: 83 -> 62 us).  Barriers:
+//   full[s]   (leader's) both CTAs' TMA loads complete_tx here;   empty[s] (each CTA's) multicast commit frees stage s
+//   tfull[b]  (each CTA's) multicast commit: accumulator set b done;   tempty[b] (leader's) 2 x 8 epilogue warps arrive
+template <int BK, bool kHasRes, bool kPair>
 __global__ void __launch_bounds__(kThreadsP, 1)
 conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_bh,
@@ -354,7 +407,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   float* ss_all = (float*)(smem_raw + 4096);       // [tile & 3][scale | shift][kMaxBNP]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + kBookBytesP + 1023) & ~(uintptr_t)1023);
   const int mh = g.mh;
-  const int b_bytes = g.BN * BK * 2;
+  const int b_bytes = (kPair ? (g.BN >> 1) : g.BN) * BK * 2;   // a pair member stages half of the weight rows
   const int stage_bytes = mh * kABytes + b_bytes;  // multiple of 1024 (BN % 16 == 0)
   uint8_t* slabs = smem + (size_t)g.n_stages_p * stage_bytes;   // [kEpiWarps][32 rows][kSlabPitch]
   // residual tiles (kHasRes && g.res_tma): [2 buffers][BN/64 boxes][128 rows x 128 B, 128B-swizzled], 1024-aligned
@@ -368,17 +421,18 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   // Cluster of 2 CTAs (two neighbouring SMs) on adjacent M tiles of the same N tile: each CTA fetches half of the
   // weight tile and TMA-multicasts it into both CTAs' shared memory, so the weight traffic out of L2 -- the larger
   // share for wide-N 1x1x1 layers -- is halved.  A stage may only be refilled when BOTH consumers released it.
-  const bool cl2 = g.cluster == 2;
-  const uint32_t crank = cl2 ? cluster_ctarank() : 0;
-  const int tile_step = cl2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int tile_first = cl2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const bool cl2 = !kPair && g.cluster == 2;
+  const bool two = kPair || cl2;                   // the grid is made of CTA pairs
+  const uint32_t crank = two ? cluster_ctarank() : 0;
+  const int tile_step = two ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tile_first = two ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < g.n_stages_p; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], cl2 ? 2 : 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiWarps);
+      mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kPair ? 2 * kEpiWarps : kEpiWarps);
       mbar_init(&rfull_bar[b], 1); mbar_init(&rempty_bar[b], kEpiWarps);
     }
     if (kHasRes) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
@@ -388,18 +442,23 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   while (ncols < (uint32_t)g.BN) ncols <<= 1;
   const uint32_t alloc_cols = ncols * (uint32_t)(mh * nbuf);   // <= 512 by construction (host)
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(alloc_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(alloc_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(alloc_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (cl2) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast into them
+  if (two) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
   // tile -> (m tile, n offset).  In a cluster the two CTAs take M tiles 2*pm and 2*pm+1 of the same N tile (the odd
   // one may lie past the end: its loads are zero-filled and nothing is stored, but it still runs the k loop).
-  auto tile_mt = [&](int tile) { const int pm = tile / g.n_tiles; return cl2 ? pm * 2 + (int)crank : pm; };
+  auto tile_mt = [&](int tile) { const int pm = tile / g.n_tiles; return two ? pm * 2 + (int)crank : pm; };
   auto tile_n0 = [&](int tile) { return (tile % g.n_tiles) * g.BN; };
 
   if (warp == 0) {
@@ -434,9 +493,16 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           const int kw = tap % g.KW, kh = (tap / g.KW) % g.KH, kt = tap / (g.KW * g.KH);
           for (int kc = 0; kc < g.kblocks_per_tap; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], tx_bytes);
             uint8_t* st = smem + (size_t)stage * stage_bytes;
             const int c0 = kc * BK;
+            if constexpr (kPair) {
+              // both CTAs' bytes are counted on the leader's barrier; my A rows and my half of the weight rows
+              if (crank == 0) mbar_expect_tx(&full_bar[stage], 2u * tx_bytes);
+              if (g.mode == A_LINEAR) tma2_load_2d(&map_a, &full_bar[stage], st, c0, (int)ho[0].m0);
+              else tma2_load_im2col_5d(&map_a, &full_bar[stage], st, c0, iw[0], ih[0], it[0], in_[0], (uint16_t)kw, (uint16_t)kh, (uint16_t)kt);
+              tma2_load_3d(&map_bh, &full_bar[stage], st + kABytes, c0, tap, n0 + (int)crank * (g.BN >> 1));
+            } else {
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
             for (int h = 0; h < mh; ++h) {
               void* a_dst = st + h * kABytes;
               if (g.mode == A_LINEAR) {
@@ -456,6 +522,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             } else {
               tma_load_3d(&map_b, &full_bar[stage], st + mh * kABytes, c0, tap, n0);
             }
+            }
             if (++stage == g.n_stages_p) { stage = 0; phase ^= 1; }
           }
         }
@@ -464,7 +531,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // one thread runs the whole loop; descriptor high words are constants, low words advance by adds (see above)
-    if (elect_one()) {
+    if ((!kPair || crank == 0) && elect_one()) {   // in a pair the leader issues for both CTAs
       constexpr uint64_t kLayout = BK == 64 ? 2 : (BK == 32 ? 4 : 6);
       constexpr uint64_t kDescHi = ((uint64_t)((8 * BK * 2) >> 4) << 32) | (1ULL << 46) | (kLayout << 61);
       const uint32_t st_lo0 = (smem_u32(smem) & 0x3FFFF) >> 4, st_step = (uint32_t)stage_bytes >> 4;
@@ -475,7 +542,8 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
         const int buf = nbuf == 2 ? (it & 1) : 0;
         const uint32_t use = (uint32_t)(nbuf == 2 ? (it >> 1) : it);
-        mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // the epilogue has drained this accumulator set
+        // the epilogue (of both CTAs in a pair) has drained this accumulator set
+        if (kPair) mbar_wait_cluster(&tempty_bar[buf], (use & 1u) ^ 1u); else mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * mh) * ncols;
         int kc = 0;
@@ -486,6 +554,13 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           const uint32_t b_lo = st_lo + b_off;
           const int nk = (kc == g.kblocks_per_tap - 1) ? g.k_tail_steps : BK / 16;   // zero-filled channel tail: no MMA
           if (++kc == g.kblocks_per_tap) kc = 0;
+          if constexpr (kPair) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              if (k < nk)
+                umma2_f16(tmem_d, kDescHi | (uint64_t)(st_lo + 2 * k), kDescHi | (uint64_t)(b_lo + 2 * k), idesc, k ? 1u : acc0);
+            umma2_commit(&empty_bar[stage]);
+          } else {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             if (k < nk)
@@ -498,10 +573,11 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                          k ? 1u : acc0);
           }
           if (cl2) umma_commit_mcast(&empty_bar[stage], (uint16_t)3); else umma_commit(&empty_bar[stage]);
+          }
           st_lo += st_step;
           if (++stage == g.n_stages_p) { stage = 0; phase ^= 1; st_lo = st_lo0; }
         }
-        umma_commit(&tfull_bar[buf]);
+        if (kPair) umma2_commit(&tfull_bar[buf]); else umma_commit(&tfull_bar[buf]);
       }
     }
     __syncwarp();
@@ -624,7 +700,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (last) mbar_arrive(&tempty_bar[buf]);   // accumulator fully read by this warp
+            if (last) { if (kPair) mbar_arrive_remote(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]); }   // accumulator fully read by this warp
             for (int h = 0; h * 16 < (w32 ? 16 : cw); ++h) {   // one 32-column box, or one 16-column box per half
               const int gc = nbase + cb + h * 16;
               if (gc >= g.Cout) break;
@@ -687,7 +763,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           // last pass: the accumulator is fully read by this warp -> hand the TMEM set back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          if (lane == 0) { if (kPair) mbar_arrive_remote(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]); }
         } else {
           __syncwarp();
         }
@@ -712,7 +788,7 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       if (ncol == 0) {  // this warp owns no columns (tiny BN): still release the accumulator
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        if (lane == 0) { if (kPair) mbar_arrive_remote(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]); }
       }
       if (res_tma) {
         __syncwarp();
@@ -723,10 +799,11 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (cl2) cluster_sync_all();   // do not exit while the peer may still multicast into / signal this CTA
+  if (two) cluster_sync_all();   // do not exit while the peer may still multicast into / signal this CTA
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(alloc_cols) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(alloc_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(alloc_cols) : "memory");
   }
 }
 
@@ -839,7 +916,18 @@ struct ConvPlan {
   dim3 grid;
   int persist_tiles;
   size_t persist_smem;
+  bool persist, pair;   // which kernel the plan was made for
 };
+
+// STEP_B200_PAIR: 0 = never use CTA pairs, 1 = wherever legal, unset = where the pair tiles fill the 74 SM pairs
+static int pair_policy() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("STEP_B200_PAIR");
+    v = !e ? -1 : (e[0] == '0' ? 0 : 1);
+  }
+  return v;
+}
 
 static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   if (int rc = load_driver_entry_points()) return rc;
@@ -865,7 +953,21 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   g.kblocks_per_tap = (p->Cin + BK - 1) / BK;
   g.k_tail_steps = (p->Cin - (g.kblocks_per_tap - 1) * BK + 15) / 16;   // the rest of the block is TMA zero fill: skip it
   long long m128 = 0;   // number of 128-row M tiles (filled in below once the A mode is known)
-  const bool persist = conv_variant() == 3 || (conv_variant() == 2 && taps == 1);
+  // CTA pairs (cta_group::2, 256-row tiles): LINEAR / IM2COL addressing, and enough 256-row tiles to fill the 74 SM pairs
+  bool pair = false;
+  if (pair_policy() != 0 && (mode == A_LINEAR || mode == A_IM2COL) && conv_variant() != 1) {
+    const long long mt = ((long long)p->N * p->OT * p->OH * p->OW + kBM - 1) / kBM;
+    const long long nt = (p->Cout + (p->residual ? kMaxBNRes : kMaxBNP) - 1) / (p->residual ? kMaxBNRes : kMaxBNP);
+    const long long pt = ((mt + 1) / 2) * nt;
+    const int num_kb = taps * g.kblocks_per_tap;
+    // Measured layer by layer (tools/experiments/r2_pair.sh, profiles/r2_conv_layers.txt): pairs win where the K loop is
+    // long enough for the operand stream to be the bound (>= 13 k-blocks of 64: 1088 -> 1024 83 -> 65 us, Mixed_5b 3x3x3
+    // 104 -> 80 us, Mixed_4 3x3x3 56 -> 45 us); short-K 1x1 layers are bound by the TMEM read-out / store side and lose
+    // (256 -> 1024: 38 -> 43 us), as do thin-input k > 1 layers, which the co-resident one-tile CTAs serve better.
+    pair = pair_policy() == 1 || (BK == 64 && num_kb >= 13 && !(taps > 1 && p->Cin <= 64) && pt >= 40);
+  }
+  const bool persist = pair || conv_variant() == 3 || (conv_variant() == 2 && taps == 1);
+  pl->pair = pair; pl->persist = persist;
   {
     // N tile: as wide as the accumulator allows -- every N tile re-reads the whole A operand through L2.
     int cap = (persist && !p->residual) ? kMaxBNP : (p->residual ? kMaxBNRes : kMaxBN);
@@ -987,8 +1089,8 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
   }
   // persistent kernel: two 128-row halves per tile when that still leaves at least one full wave of tiles
   m128 = m_tiles;
-  g.mh = (conv_variant() == 3 && ((m128 + 1) / 2) * g.n_tiles >= kNumSMs) ? 2 : 1;
-  if (const char* e = getenv("STEP_B200_MH")) { if (e[0] == '1') g.mh = 1; else if (e[0] == '2') g.mh = 2; }
+  g.mh = (!pair && conv_variant() == 3 && ((m128 + 1) / 2) * g.n_tiles >= kNumSMs) ? 2 : 1;
+  if (const char* e = getenv("STEP_B200_MH")) { if (!pair) { if (e[0] == '1') g.mh = 1; else if (e[0] == '2') g.mh = 2; } }
   {
     int ncols = 32;
     while (ncols < g.BN) ncols <<= 1;
@@ -997,7 +1099,7 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
     g.res_bufs = g.BN > 128 ? 1 : 2;
     const size_t res_bytes = g.res_tma ? (size_t)g.res_bufs * (g.BN / 64) * kBM * 128 + 1024 : 0;
     const size_t budget = 227 * 1024 - kBookBytesP - 1024 - (size_t)kEpiWarps * kSlabBytes - res_bytes;
-    const size_t stage_bytes = (size_t)g.mh * kBM * BK * 2 + (size_t)g.BN * BK * 2;
+    const size_t stage_bytes = (size_t)g.mh * kBM * BK * 2 + (size_t)(pair ? g.BN / 2 : g.BN) * BK * 2;
     int st = (int)(budget / stage_bytes);
     g.n_stages_p = st > kMaxStagesP ? kMaxStagesP : st;
     if (const char* e = getenv("STEP_B200_STAGES")) { int v = atoi(e); if (v >= 2 && v < g.n_stages_p) g.n_stages_p = v; }
@@ -1008,9 +1110,10 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
       // measured (tools/conv_bench.py, STEP_B200_CLUSTER=1|2): no gain on B200 -- the wide-N 1x1x1 layers are not
       // bound by the weight traffic out of L2 -- so the multicast path is opt-in (validated by tests/test_gpu_conv.py)
       const bool want = e ? (e[0] == '2') : false;
-      if (want && persist && g.mh == 1 && m128 >= 2 * 74 && g.BN >= 64 && (g.BN / 2) % 8 == 0) g.cluster = 2;
+      if (want && !pair && persist && g.mh == 1 && m128 >= 2 * 74 && g.BN >= 64 && (g.BN / 2) % 8 == 0) g.cluster = 2;
     }
-    pl->persist_tiles = g.cluster == 2 ? (int)(((m128 + 1) / 2) * g.n_tiles) : (int)(((m128 + g.mh - 1) / g.mh) * g.n_tiles);
+    pl->persist_tiles = (pair || g.cluster == 2) ? (int)(((m128 + 1) / 2) * g.n_tiles) : (int)(((m128 + g.mh - 1) / g.mh) * g.n_tiles);
+    if (pair) g.idesc = (1u << 4) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);   // M = 256 across the pair
     // epilogue column split between the two warp groups (mh == 1) and the store path
     {
       const char* e = getenv("STEP_B200_TMAST");
@@ -1047,7 +1150,7 @@ static int build_plan(const step_conv_params* p, ConvPlan* pl) {
       }
     }
     pl->map_bh = pl->map_b;
-    if (g.cluster == 2) {
+    if (g.cluster == 2 || pair) {
       cuuint64_t bdims[3] = {(cuuint64_t)p->Cin, (cuuint64_t)taps, (cuuint64_t)p->Cout};
       cuuint64_t bstr[2] = {(cuuint64_t)p->w_ld * 2, (cuuint64_t)taps * p->w_ld * 2};
       cuuint32_t bbox[3] = {(cuuint32_t)BK, 1, (cuuint32_t)(g.BN / 2)};
@@ -1087,17 +1190,17 @@ static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t
   return 0;
 }
 
-template <int BK, bool kHasRes>
+template <int BK, bool kHasRes, bool kPair>
 static int launch_persist(const ConvPlan& pl, const step_conv_params* p, cudaStream_t s) {
   static std::atomic<unsigned long long> attr_seen{0};
   if (first_use_on_device(attr_seen)) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_persist_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_persist_kernel<BK, kHasRes, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv3d(f16): smem attribute: %s", cudaGetErrorString(e));
   }
   const int total = pl.persist_tiles;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
-  if (pl.g.cluster == 2) {
+  if (pl.g.cluster == 2 || kPair) {
     const int pairs = total < kNumSMs / 2 ? total : kNumSMs / 2;
     cfg.gridDim = dim3(2 * pairs);
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1109,11 +1212,11 @@ static int launch_persist(const ConvPlan& pl, const step_conv_params* p, cudaStr
   cfg.blockDim = dim3(kThreadsP);
   cfg.dynamicSmemBytes = pl.persist_smem;
   cfg.stream = s;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_umma_persist_kernel<BK, kHasRes>, pl.map_a, pl.map_b, pl.map_r, pl.map_bh, pl.map_y[0], pl.map_y[1],
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_umma_persist_kernel<BK, kHasRes, kPair>, pl.map_a, pl.map_b, pl.map_r, pl.map_bh, pl.map_y[0], pl.map_y[1],
                                       pl.map_y[2], pl.g,
                                       total, p->scale, p->shift, (const __half*)p->residual, (__half*)p->y);
   if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "conv_umma_persist_kernel launch: %s", cudaGetErrorString(le)); }
-  STEP_LAUNCH_CHECK("conv_umma_persist_kernel");
+  STEP_LAUNCH_CHECK(kPair ? "conv_umma_persist_kernel(pair)" : "conv_umma_persist_kernel");
   return 0;
 }
 
@@ -1125,10 +1228,15 @@ int conv3d_umma_launch(const step_conv_params* p, step_stream_t stream) {
   // loops: per-CTA setup + epilogue dominate, wide N tiles); for k > 1 the one-tile-per-CTA kernel with 2-5
   // co-resident CTAs per SM keeps more TMA requests in flight and wins, by 2x on the BK=32 stem.
   // STEP_B200_CONV=1 forces one-tile-per-CTA everywhere, =3 forces the persistent kernel everywhere.
-  if (conv_variant() == 3 || (conv_variant() == 2 && pl.g.taps == 1)) {
-    if (pl.BK == 64) return res ? launch_persist<64, true>(pl, p, cu(stream)) : launch_persist<64, false>(pl, p, cu(stream));
-    if (pl.BK == 32) return res ? launch_persist<32, true>(pl, p, cu(stream)) : launch_persist<32, false>(pl, p, cu(stream));
-    return res ? launch_persist<16, true>(pl, p, cu(stream)) : launch_persist<16, false>(pl, p, cu(stream));
+  if (pl.pair) {
+    if (pl.BK == 64) return res ? launch_persist<64, true, true>(pl, p, cu(stream)) : launch_persist<64, false, true>(pl, p, cu(stream));
+    if (pl.BK == 32) return res ? launch_persist<32, true, true>(pl, p, cu(stream)) : launch_persist<32, false, true>(pl, p, cu(stream));
+    return res ? launch_persist<16, true, true>(pl, p, cu(stream)) : launch_persist<16, false, true>(pl, p, cu(stream));
+  }
+  if (pl.persist) {
+    if (pl.BK == 64) return res ? launch_persist<64, true, false>(pl, p, cu(stream)) : launch_persist<64, false, false>(pl, p, cu(stream));
+    if (pl.BK == 32) return res ? launch_persist<32, true, false>(pl, p, cu(stream)) : launch_persist<32, false, false>(pl, p, cu(stream));
+    return res ? launch_persist<16, true, false>(pl, p, cu(stream)) : launch_persist<16, false, false>(pl, p, cu(stream));
   }
   if (pl.BK == 64) return res ? launch_bk<64, true>(pl, p, cu(stream)) : launch_bk<64, false>(pl, p, cu(stream));
   if (pl.BK == 32) return res ? launch_bk<32, true>(pl, p, cu(stream)) : launch_bk<32, false>(pl, p, cu(stream));

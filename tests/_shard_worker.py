@@ -1,0 +1,60 @@
+"""torchrun worker for tests/test_gpu_multi.py: rank r runs clips [r*B, (r+1)*B) of a seeded 2B-clip stream through the
+captured step (trunk -> 3 refinement steps -> device post-processing) and the fixed-shape detections are gathered with ONE
+NCCL all_gather_into_tensor.  Rank 0 saves what it gathered."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import step_b200  # noqa: E402
+from step_b200 import synth  # noqa: E402
+
+
+def build(cfg, dev):
+    nets = {"base_net": step_b200.BaseNet(cfg), "roi_net": step_b200.ROINet(cfg.pool_mode, cfg.pool_size)}
+    nets["base_net"].load_state_dict(synth.base_net_state_dict())
+    for i in range(cfg.max_iter):
+        h = step_b200.TwoBranchNet(cfg)
+        h.load_state_dict(synth.head_state_dict(100 + i, cfg))
+        nets["det_net%d" % i] = h
+    for k in nets:
+        nets[k] = nets[k].to(dev).eval()
+        if hasattr(nets[k], "set_device"):
+            nets[k].set_device(dev)
+    return nets
+
+
+def run_shard(dev, clips, B, T_in, HW, N, detect):
+    cfg = synth.make_cfg(fp16=True, T=T_in // 4, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 1}, image_size=(HW, HW))
+    nets = build(cfg, dev)
+    tubes = synth.make_proposals(B, N, cfg.T, HW, HW)
+    runner = step_b200.StepRunner(cfg, nets, B, T_in, HW, HW, tubes, device=dev, detect=detect)
+    with torch.no_grad():
+        runner(clips.to(dev))
+    d = runner.detections[cfg.max_iter - 1]
+    return torch.cat([d["det"].view(B, -1), d["count"].view(B, 1).float()], dim=1).contiguous()
+
+
+def main():
+    out_path, B, T_in, HW, N = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    clips = synth.make_clips(world * B, T_in, HW, HW, seed=77)[rank * B:(rank + 1) * B].contiguous()
+    det = run_shard(dev, clips, B, T_in, HW, N, dict(conf_thresh=0.01, nms_thresh=0.4, topk=50))
+    gathered = torch.empty((world,) + tuple(det.shape), dtype=det.dtype, device=dev)
+    dist.all_gather_into_tensor(gathered.view(-1, det.shape[1]), det)
+    torch.cuda.synchronize()
+    if rank == 0:
+        np.save(out_path, gathered.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,13 @@ LAYERS = {
     "loc_1024":   (704, 1, 7, 7, 1024, 256, (1, 1, 1), None, False),
     "5b_fused":   (88, 8, 7, 7, 832, 448, (1, 1, 1), None, False),
     "4b_fused":   (8, 8, 14, 14, 480, 304, (1, 1, 1), None, False),
+    "conv2b":     (8, 16, 56, 56, 64, 64, (1, 1, 1), None, False),
+    "3b_fused":   (8, 16, 28, 28, 192, 176, (1, 1, 1), None, False),
+    "3c_fused":   (8, 16, 28, 28, 256, 288, (1, 1, 1), None, False),
+    "3c_b3":      (8, 16, 28, 28, 256, 64, (1, 1, 1), None, False),
+    "4c_fused":   (8, 8, 14, 14, 512, 296, (1, 1, 1), None, False),
+    "5c_fused":   (88, 8, 7, 7, 832, 624, (1, 1, 1), None, False),
+    "5b_b3":      (88, 8, 7, 7, 832, 128, (1, 1, 1), None, False),
 }
 names = sys.argv[1:] or list(LAYERS)
 torch.manual_seed(0)
@@ -51,4 +58,19 @@ for name in names:
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
     gf = 2.0 * N * T * H * W * Cin * Cout * k[0] * k[1] * k[2] / 1e9
-    print("%-10s %8.1f us  %7.1f TFLOP/s  %4.1f%% of 1451 (algorithmic %.1f GFLOP)" % (name, us, gf / us * 1e3, gf / us * 1e3 / 14.511, gf))
+    # spot check against torch on a sample of output pixels (tool only: the parity tests live in tests/)
+    err = -1.0
+    if os.environ.get("CB_CHECK", "1") == "1":
+        import torch.nn.functional as F
+        n_s = min(N, 2)
+        xs = x.buf[:n_s].float().permute(0, 4, 1, 2, 3)
+        ws = w.float().view(Cout, k[0], k[1], k[2], Cin).permute(0, 4, 1, 2, 3)
+        pd = pad if pad is not None else tuple(E.same_pad(kk, 1)[0] for kk in k)
+        hi = tuple(kk - 1 - q for kk, q in zip(k, pd))
+        xp = F.pad(xs, (pd[2], hi[2], pd[1], hi[1], pd[0], hi[0]))
+        ref = F.conv3d(xp, ws).permute(0, 2, 3, 4, 1)
+        if res:
+            ref = ref + r.buf[:n_s].float()
+        ref = torch.relu(ref)
+        err = float((out.buf[:n_s].float() - ref).abs().max() / ref.abs().max())
+    print("%-10s %8.1f us  %7.1f TFLOP/s  %4.1f%% of 1451 (algorithmic %.1f GFLOP)  rel_err %.1e" % (name, us, gf / us * 1e3, gf / us * 1e3 / 14.511, gf, err))
