@@ -406,13 +406,21 @@ def parity_vs_oracle(gpu, ref_out, cfg, W):
         r_loc = otubes.valid_tubes(h["pred_loc"][:N].numpy().copy(), W["HW"], W["HW"])
         b_px = max(b_px, float(np.abs(g_loc - r_loc).max()))
     out["score_abs"], out["box_px"] = round(s_abs, 6), round(b_px, 4)
-    def det_set(prob, centre_boxes):
-        d = opp.detections(prob, centre_boxes, [N], DETECT["conf_thresh"], DETECT["nms_thresh"], float(W["HW"]), float(W["HW"]),
+    def det_set(prob, centre_boxes, nms_thr=DETECT["nms_thresh"]):
+        d = opp.detections(prob, centre_boxes, [N], DETECT["conf_thresh"], nms_thr, float(W["HW"]), float(W["HW"]),
                            topk=DETECT["topk"])[0]
         out_ = set()
         for bx, c, sc in d:   # the rows carry no tube index: recover it from the score
             out_.add((int(c), int(np.argmin(np.abs(prob[:, c] - sc)))))
         return out_
+
+    def pair_ious(boxes):
+        b = otubes.valid_tubes(boxes.reshape(-1, 1, 4).copy()).reshape(-1, 4).astype(np.float64)   # test.py:191
+        area = (b[:, 2] - b[:, 0] + 1) * (b[:, 3] - b[:, 1] + 1)
+        w = np.maximum(0, np.minimum(b[:, None, 2], b[None, :, 2]) - np.maximum(b[:, None, 0], b[None, :, 0]) + 1)
+        h = np.maximum(0, np.minimum(b[:, None, 3], b[None, :, 3]) - np.maximum(b[:, None, 1], b[None, :, 1]) + 1)
+        iou = w * h / (area[:, None] + area[None, :] - w * h)
+        return iou[np.triu_indices(b.shape[0], 1)]
     last = hist[-1]
     mid = last["pred_loc"].shape[1] // 2
     r_prob, r_loc = last["pred_prob"][:N, 0].numpy(), last["pred_loc"][:N].numpy()            # clamped in place by the CPU run
@@ -425,6 +433,17 @@ def parity_vs_oracle(gpu, ref_out, cfg, W):
     out["nms_keep_equal"] = len(diff) == 0
     out["detections_ref"], out["detections_gpu"], out["detections_differing"] = len(ref_set), len(gpu_set), len(diff)
     out["differing_within_1e-3_of_conf_thresh"] = borderline
+    # Boxes are shared by all classes, so ONE box pair whose IoU sits at the NMS threshold flips the kept set of every
+    # class at once under <= 0.4 px of fp16 box noise.  Say how many such pairs this synthetic scene has, and compare the
+    # sets again with the threshold moved to the middle of the widest IoU gap near it (a scene-independent statement).
+    ious = np.sort(pair_ious(r_loc[:, mid].copy()))
+    out["ref_box_pairs_with_iou_within_0.01_of_nms_thresh"] = int((np.abs(ious - DETECT["nms_thresh"]) < 0.01).sum())
+    near = ious[(ious > DETECT["nms_thresh"] - 0.1) & (ious < DETECT["nms_thresh"] + 0.1)]
+    if near.size >= 2:
+        k = int(np.argmax(np.diff(near)))
+        gap_thr = float(0.5 * (near[k] + near[k + 1]))
+        out["gap_nms_thresh"] = round(gap_thr, 4)
+        out["nms_keep_equal_at_gap_thresh"] = det_set(r_prob, r_loc[:, mid].copy(), gap_thr) == det_set(g_prob, g_loc[:, mid].copy(), gap_thr)
     # the device post-processing that ran inside the timed step == the reference loop on the same (GPU) history
     in_graph = set((int(r[5]), int(r[6])) for r in gpu["det"][:gpu["cnt"]])
     out["device_detect_equals_reference_loop"] = in_graph == det_set(g_prob, g_loc_raw[:, mid].copy())

@@ -212,6 +212,34 @@ int step_head_regress(const void* x, int dtype, int R, int T, int K, int x_ld, c
                       int s0, int s1, int e0, int e1, float* local_loc, float* first, float* last, void* workspace,
                       size_t ws_bytes, step_stream_t stream);
 
+/* ------------------------------------------------------------------ training (first pieces) ---- */
+/* TwoBranchNet's losses (models/two_branch.py:276-333) and, when the d* pointers are given, the gradient of the training
+ * objective mean(loss_cls) + w_loc * loss_loc + w_nb * loss_nb (train.py:323-347) with respect to the head outputs.
+ *   logits [N,cls] (pre-sigmoid), local_loc [N,T_len,4], first_loc / last_loc [N,Tc,4], tubes [N,T_len,5],
+ *   targets [N,3,6+cls] = (first, centre, last) x (box 4 | cls mask | loc mask | labels).
+ * loss_cls [N*cls] holds the element-wise BCE (all zeros when no sample is positive: flags[0] = 0 and the reference then
+ * returns the scalar 0), loss_loc / loss_nb [1]; flags [3] = {cls, loc, neighbour mask sums non-zero}.
+ * dloc [N,T_len,4] already includes what flows back through the first / last slices.  scratch: N*12 floats. */
+int step_head_losses_f32(const float* logits, const float* local_loc, const float* first_loc, const float* last_loc,
+                         const float* tubes, const float* targets, int N, int cls, int T_len, int T, int Tc, float w_loc,
+                         float w_nb, float* loss_cls, float* loss_loc, float* loss_nb, int* flags, float* dlogits,
+                         float* dloc, float* dfirst, float* dlast, float* scratch, step_stream_t stream);
+/* Channels-last ROIAlign backward without atomics (replaces _C.roi_align_backward, vision.cpp:33 /
+ * cuda/ROIAlign_cuda.cu:201-278, whose atomicAdd scatter is not repeatable): grad_out [R,ph,pw,C] (channel stride
+ * out_ld, STEP_F32 / STEP_F16) -> grad_in [K,H,W,C] fp32 (channel stride in_ld), written completely by the call. */
+int step_roi_align_bwd_nhwc(const void* grad_out, int dtype, int out_ld, const float* rois, int R, float scale, int ph,
+                            int pw, int K, int H, int W, int C, int sampling_ratio, float* grad_in, int in_ld,
+                            step_stream_t stream);
+/* Backward of y = x W^T + b for the small-N linears of the head (nn.Linear / global_cls, two_branch.py:246-270):
+ * dx [M,K] (+)= dy W, dw [Nn,K] = dy^T x, db [Nn] = column sums of dy; any of dx / dw may be NULL.  Fixed summation order. */
+int step_linear_small_n_bwd(const void* x, int dtype, int M, int K, int x_ld, const float* w, const float* dy, int Nn,
+                            float* dx, int dx_accumulate, float* dw, float* db, step_stream_t stream);
+/* Weight gradient of a 1x1(x1) convolution: dw[Cout,Cin] (+)= scale * sum_m dz[m,co] x[m,ci]; fp16 operands, fp32
+ * tensor-core accumulation, pixel chunks reduced in a fixed order (deterministic). */
+size_t step_conv1x1_wgrad_workspace_bytes(int M, int Cout, int Cin);
+int step_conv1x1_wgrad_f16(const void* dz, int dz_ld, const void* x, int x_ld, int M, int Cout, int Cin, float scale,
+                           float* dw, int dw_ld, int accumulate, void* workspace, size_t ws_bytes, step_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

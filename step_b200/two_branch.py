@@ -3,8 +3,9 @@ state_dict keys (models/two_branch.py:113-373), running on libstep_b200.so.
 
 TwoBranchNet.forward(global_feat[R,T',832,7,7], context_feat=None|[R,1024,T',1,1], tubes, targets)
   -> (global_prob[R,cls], local_loc[R,T',4], first_loc[R,T,4], last_loc[R,T,4], loss x3)
-Inference only (targets must be None): the three losses are returned as zeros exactly as the
-reference does when targets is None (two_branch.py:278-280, 338-340).
+With targets=None the three losses are returned as zeros exactly as the reference does
+(two_branch.py:278-280, 338-340); with targets they are computed on the device (step_b200/training.py::head_losses,
+eval-mode dropout).  The outputs carry no grad_fn: the backward of the convolutions is not built yet.
 
 Layout tricks (none changes results beyond fp rounding):
   * ROI features and the 1x1x1 `downsample` output share one [R*T',7,7,1088] buffer, so the concat
@@ -225,9 +226,6 @@ class TwoBranchNet(nn.Module):
 
     # ---- forward ------------------------------------------------------------------------------
     def forward(self, global_feat, context_feat=None, tubes=None, targets=None):
-        if targets is not None:
-            raise NotImplementedError("step_b200.TwoBranchNet: training losses (two_branch.py:276-333) are the "
-                                      "'next' row of SURVEY.md section 8f; inference only")
         dev = self.device
         if dev is not None and str(dev) != "cpu":
             global_feat = global_feat.to(dev)
@@ -246,11 +244,25 @@ class TwoBranchNet(nn.Module):
                 cf = context_feat.detach().float().contiguous().view(N * context_feat.shape[1], T)
                 # mean over T' of [N*1024, T', 1] -> [N, 1024]
                 ctx_mean = E.mean_mid(cf.data_ptr(), L.F32, N * context_feat.shape[1], T, 1, 1, 1, cf.device).view(N, -1)
-            prob, loc, first, last = self.forward_act(cat, ctx_mean, None)
+            if targets is None:
+                prob, loc, first, last = self.forward_act(cat, ctx_mean, None)
+            else:
+                prob, loc, first, last, logits = self.forward_act(cat, ctx_mean, None, want_logits=True)
         z = torch.tensor(0., device=prob.device)
-        return prob, loc, first, last, z.view(-1), z.view(-1), z.view(-1)
+        if targets is None:
+            return prob, loc, first, last, z.view(-1), z.view(-1), z.view(-1)
+        # training-time outputs (two_branch.py:276-341), eval-mode dropout; the losses are computed on the device.
+        # NOTE: the outputs carry no grad_fn -- the backward of the convolutions is not built yet (step_b200/training.py).
+        from . import training
+        if tubes is None:
+            raise RuntimeError("TwoBranchNet.forward: targets need tubes")
+        if self.cls_only:
+            raise NotImplementedError("TwoBranchNet(cls_only=True).forward(targets=...) is not built")
+        tb, tg = tubes.to(prob.device), targets.to(prob.device)
+        lc, ll, ln = training.head_losses(logits, loc, first, last, tb, tg, self.T)
+        return prob, loc, first, last, lc, ll, ln
 
-    def forward_act(self, cat, ctx_mean=None, ctx_row_map=None):
+    def forward_act(self, cat, ctx_mean=None, ctx_row_map=None, want_logits=False, keep=None):
         """cat: Act [R, T', 7, 7, ld >= 832 + fc] whose first 832 channels hold the ROI features.
         ctx_mean: fp32 [rows, 1024] temporal mean of the context feature; ctx_row_map: int32 [R]
         row of ctx_mean for each tube (None = identity).  Returns fp32 tensors."""
@@ -274,9 +286,15 @@ class TwoBranchNet(nn.Module):
             E.linear_small_n(ctx_mean, R, 1024, 1024, hw["ctx_w"], None, self.num_classes, y=logits, act=1,
                              accumulate=True, row_map=ctx_row_map)
         prob = logits
+        raw = None
+        if want_logits:   # the losses take the pre-sigmoid class scores (two_branch.py:296): same GEMV without the sigmoid
+            raw = E.linear_small_n(xbar, R, D, D, hw["cls_w"], hw["cls_b"], self.num_classes, act=0)
+            if has_ctx:
+                E.linear_small_n(ctx_mean, R, 1024, 1024, hw["ctx_w"], None, self.num_classes, y=raw, act=0,
+                                 accumulate=True, row_map=ctx_row_map)
         if self.cls_only:
             z = torch.tensor([0.], device=prob.device)
-            return prob, z, z, z
+            return (prob, z, z, z, raw) if want_logits else (prob, z, z, z)
         # local branch on frames (two_branch.py:253-262)
         lf = self.local_conv(cat.frames())
         w2, b2 = _packed(self.downsample2, code)
@@ -297,7 +315,9 @@ class TwoBranchNet(nn.Module):
         ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=cat.device)
         L.check(L.lib().step_head_regress(L.ptr(lf2.buf), code, R, T, D, D, L.ptr(w12), L.ptr(b12), s0, s1, e0, e1,
                                           L.ptr(local_loc), L.ptr(first), L.ptr(last), L.ptr(ws), nbytes, L.stream()))
-        return prob, local_loc, first, last
+        if keep is not None:   # activations the training pieces need (step_b200/training.py): channels-last layouts
+            keep.update(xbar=xbar, local_feat=lf, local_feat2=lf2, slices=(s0, s1, e0, e1))
+        return (prob, local_loc, first, last, raw) if want_logits else (prob, local_loc, first, last)
 
     def _reg12(self, code):
         """[W_local | W_nb1 | W_nb2] (12 x D, permuted to channels-last) in the compute dtype + fp32 biases."""

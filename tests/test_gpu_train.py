@@ -1,0 +1,215 @@
+"""GPU: the training pieces (step_b200/training.py, csrc/train.cu) against the reference's outputs
+(tests/golden/losses_cases.npz, head_grads.npz: TwoBranchNet.forward(targets=...) and its autograd in the reference),
+torch-CPU autograd of the oracle, and torchvision's ROIAlign backward (tests/golden/roi_cross_cases.npz).
+
+Tolerances: fp32 losses 1e-4 relative (expf / log1pf / logf are not bit-exact); gradients through fp16 activations
+2e-2 of the tensor norm."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as om
+from step_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def head(cfg):
+    import step_b200
+    h = step_b200.TwoBranchNet(cfg)
+    h.load_state_dict(synth.head_state_dict(100, cfg), strict=True)
+    h = h.cuda().eval()
+    h.set_device("cuda:0")
+    return h
+
+
+@pytest.mark.parametrize("name", list(synth.LOSS_CASES))
+def test_forward_with_targets_matches_reference(golden, name):
+    """TwoBranchNet.forward(feat, None, tubes=..., targets=...) -- the training-time call of train.py:323 -- on the fp32
+    path against the reference's outputs for the same seeded inputs (prob, loc, first, last and the three losses)."""
+    g = golden("losses_cases")
+    T_, chunks, _, _ = synth.LOSS_CASES[name]
+    cfg = synth.make_cfg(fp16=False, T=T_, max_iter=1, NUM_CHUNKS={1: chunks}, image_size=(112, 112))
+    _, _, feat, tb, tg = synth.make_loss_case(name, cfg.num_classes)
+    net = head(cfg)
+    with torch.no_grad():
+        prob, loc, first, last, lc, ll, ln = net(feat.cuda(), None, tubes=tb.cuda(), targets=tg.cuda())
+    torch.cuda.synchronize()
+    assert np.allclose(prob.cpu().numpy(), g[name + "_prob"], rtol=1e-4, atol=2e-5)
+    assert np.allclose(loc.cpu().numpy(), g[name + "_loc"], rtol=1e-4, atol=2e-5)
+    assert np.allclose(first.cpu().numpy(), g[name + "_first"], rtol=1e-4, atol=2e-5)
+    assert np.allclose(last.cpu().numpy(), g[name + "_last"], rtol=1e-4, atol=2e-5)
+    assert tuple(lc.shape) == tuple(g[name + "_loss_cls"].shape)
+    assert np.allclose(lc.cpu().numpy(), g[name + "_loss_cls"], rtol=1e-4, atol=2e-6)
+    assert np.allclose(ll.cpu().numpy(), g[name + "_loss_loc"], rtol=1e-4, atol=2e-6)
+    assert np.allclose(ln.cpu().numpy(), g[name + "_loss_nb"], rtol=1e-4, atol=2e-6)
+    if name == "nomask":
+        assert lc.numel() == 1 and float(lc) == 0.0 and float(ll) == 0.0 and float(ln) == 0.0
+
+
+@pytest.mark.parametrize("name", ["c1", "c3"])
+def test_loss_gradients_match_autograd(name):
+    """d(mean(loss_cls) + 5 loss_loc + loss_nb)/d(head outputs) from the fused kernel vs torch autograd through the oracle's
+    losses (oracle/model.py::two_branch_losses, pinned to the reference by tests/test_oracle.py)."""
+    from step_b200 import training
+    T_, chunks, n, _ = synth.LOSS_CASES[name]
+    _, _, _, tb, tg = synth.make_loss_case(name, 60)
+    gen = torch.Generator().manual_seed(5)
+    Tl = T_ * chunks
+    half = T_ // 2
+    s0, e0 = 0, (chunks - 1) * T_
+    logits = torch.randn(n, 60, generator=gen).requires_grad_(True)
+    loc = (torch.randn(n, Tl, 4, generator=gen) * 0.7).requires_grad_(True)       # some |d| > 1: both smooth-L1 branches
+    nb1 = (torch.randn(n, T_, 4, generator=gen) * 0.3).requires_grad_(True)
+    nb2 = (torch.randn(n, T_, 4, generator=gen) * 0.3).requires_grad_(True)
+    first = loc[:, s0:s0 + T_] + nb1
+    last = loc[:, e0:e0 + T_] + nb2
+    lc, ll, ln = om.two_branch_losses(logits, loc, first, last, tb, tg, T_)
+    (lc.mean() + 5.0 * ll.mean() + 1.0 * ln.mean()).backward()
+    out = training.head_losses(logits.detach().cuda(), loc.detach().cuda(), first.detach().cuda(), last.detach().cuda(),
+                               tb.cuda(), tg.cuda(), T_, lambda_reg=5.0, lambda_neighbor=1.0, want_grads=True)
+    lcg, llg, lng, g = out
+    assert np.allclose(lcg.cpu().numpy(), lc.detach().numpy(), rtol=1e-4, atol=1e-6)
+    assert np.allclose(llg.cpu().numpy(), ll.detach().numpy(), rtol=1e-4, atol=1e-6)
+    assert np.allclose(lng.cpu().numpy(), ln.detach().numpy(), rtol=1e-4, atol=1e-6)
+    assert np.allclose(g["logits"].cpu().numpy(), logits.grad.numpy(), rtol=1e-4, atol=1e-8)
+    assert np.allclose(g["local_loc"].cpu().numpy(), loc.grad.numpy(), rtol=1e-4, atol=1e-8)
+    assert np.allclose(g["first_loc"].cpu().numpy(), nb1.grad.numpy(), rtol=1e-4, atol=1e-8)
+    assert np.allclose(g["last_loc"].cpu().numpy(), nb2.grad.numpy(), rtol=1e-4, atol=1e-8)
+    # repeatable bit for bit
+    again = training.head_losses(logits.detach().cuda(), loc.detach().cuda(), first.detach().cuda(), last.detach().cuda(),
+                                 tb.cuda(), tg.cuda(), T_, want_grads=True)
+    assert all(torch.equal(again[3][k], g[k]) for k in g) and torch.equal(again[1], llg)
+
+
+def test_head_weight_gradients_match_reference_autograd(golden):
+    """Chain through the pieces that exist: losses -> dlogits / dloc -> linear backward of global_cls, local_reg,
+    neighbor_reg1/2 -> d(local feature) -> tensor-core wgrad of the 1x1 `downsample2` convolution, against the gradients
+    the reference's autograd produced for the same seeded case (tests/golden/head_grads.npz: norm + leading values).
+    Runs on the fp16 path (the wgrad kernel takes fp16 operands): 2e-2 of the norm."""
+    from step_b200 import engine as E, training
+    from step_b200.engine import Act
+    from step_b200.networks import to_act
+    from step_b200 import _lib as L
+    g = golden("head_grads")
+    name = "c1"
+    T_, chunks, n, _ = synth.LOSS_CASES[name]
+    cfg = synth.make_cfg(fp16=True, T=T_, max_iter=1, NUM_CHUNKS={1: chunks}, image_size=(112, 112))
+    _, _, feat, tb, tg = synth.make_loss_case(name, cfg.num_classes)
+    net = head(cfg)
+    N, Tl = feat.shape[0], feat.shape[1]
+    keep = {}
+    with torch.no_grad():
+        cat = Act.empty(N, Tl, 7, 7, 832 + cfg.fc_dim, L.F16, torch.device("cuda", 0))
+        src = to_act(feat.cuda(), L.F16)
+        cat.buf[..., :832].copy_(src.buf)
+        prob, loc, first, last, logits = net.forward_act(cat, None, None, want_logits=True, keep=keep)
+        lc, ll, ln, gr = training.head_losses(logits, loc, first, last, tb.cuda(), tg.cuda(), T_, 5.0, 1.0, want_grads=True)
+    loss = float(lc.mean() + 5.0 * ll.mean() + ln.mean())
+    assert abs(loss - float(g["loss"][0])) <= 2e-3 * abs(float(g["loss"][0]))
+    fc, ps = cfg.fc_dim, cfg.pool_size
+    D = fc * ps * ps
+    unperm = lambda w: w.view(-1, ps * ps, fc).permute(0, 2, 1).reshape(w.shape[0], -1)   # (p*fc + c) -> (c*49 + p)
+
+    def check(key, got, tol=2e-2):
+        ref_n = float(g["gn:" + key][0])
+        got_n = float(got.double().norm())
+        assert abs(got_n - ref_n) <= tol * ref_n, (key, got_n, ref_n)
+        head8 = got.reshape(-1)[:8].cpu().numpy()
+        assert np.abs(head8 - g["gh:" + key]).max() <= tol * max(np.abs(g["gh:" + key]).max(), ref_n / got.numel() ** 0.5), key
+
+    # global_cls: logits = mean_t(feat) . W^T + b  ->  dW = dlogits^T xbar (two_branch.py:246-249; mean taken first)
+    _, dw, db = training.linear_backward(keep["xbar"], None, gr["logits"], need_dx=False)
+    check("global_cls.weight", unperm(dw).reshape(cfg.num_classes, D, 1, 1, 1))
+    check("global_cls.bias", db)
+    # regressors: local_reg sees every frame, neighbor_reg1 / 2 the first / last chunk (two_branch.py:261-270)
+    lf2 = keep["local_feat2"].buf.view(N, Tl, D)
+    s0, s1, e0, e1 = keep["slices"]
+    hw = net._head_weights()
+    dlf2 = torch.zeros((N, Tl, D), dtype=torch.float32, device="cuda")
+    dx, dw, db = training.linear_backward(lf2.reshape(N * Tl, D), hw["local_reg_w32"], gr["local_loc"].reshape(N * Tl, 4))
+    dlf2 += dx.view(N, Tl, D)
+    check("local_reg.weight", unperm(dw)); check("local_reg.bias", db)
+    for nm, (a, b), gk in (("neighbor_reg1", (s0, s1), "first_loc"), ("neighbor_reg2", (e0, e1), "last_loc")):
+        xs = lf2[:, a:b].reshape(-1, D).contiguous()
+        dx, dw, db = training.linear_backward(xs, hw[nm + "_w32"], gr[gk].reshape(-1, 4))
+        dlf2[:, a:b] += dx.view(N, b - a, D)
+        check(nm + ".weight", unperm(dw)); check(nm + ".bias", db)
+    # downsample2 (1x1 conv, bias, no activation): dW[256, 1024] = dz^T x over the N*T'*49 pixels; db = column sums
+    dz = dlf2.view(N * Tl * ps * ps, fc).to(torch.float16).contiguous()
+    lf = keep["local_feat"]
+    x = lf.buf.view(-1, lf.ld)[:, lf.coff:lf.coff + lf.C]
+    dW = training.conv1x1_wgrad(dz, x)
+    check("downsample2.weight", dW.view(fc, 1024, 1, 1))
+    check("downsample2.bias", dlf2.view(-1, fc).sum(0))
+
+
+def test_roi_align_backward_nhwc_matches_torchvision_and_is_deterministic(golden):
+    from step_b200 import training
+    g, a = golden("roi_cross_cases"), golden("roi_align_cases")
+    K, C, H, W = a["feat"].shape
+    rois = cu(a["rois"])
+    for sr in (0, 2):
+        gy = np.zeros(g["align_gy_sr%d" % sr].shape[:1] + (8,) + g["align_gy_sr%d" % sr].shape[2:], np.float32)
+        gy[:, :C] = g["align_gy_sr%d" % sr]                       # pad 5 -> 8 channels (16-byte vectors)
+        go = cu(gy.transpose(0, 2, 3, 1))                          # [R, 7, 7, 8]
+        gin = training.roi_align_backward_nhwc(go, rois, 1.0 / 16.0, K, H, W, sr)
+        ref = g["align_gx_sr%d" % sr]
+        got = gin.cpu().numpy().transpose(0, 3, 1, 2)[:, :C]
+        assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+        assert torch.equal(gin, training.roi_align_backward_nhwc(go, rois, 1.0 / 16.0, K, H, W, sr))
+        gh = training.roi_align_backward_nhwc(go.half(), rois, 1.0 / 16.0, K, H, W, sr)
+        assert np.abs(gh.cpu().numpy().transpose(0, 3, 1, 2)[:, :C] - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())
+
+
+def test_roi_align_backward_nhwc_is_adjoint_at_pipeline_shape():
+    """<ROIAlign(x), g> == <x, ROIAlign^T(g)> at the C4 shape of one clip (8 frames of 14x14x832, 11 tubes)."""
+    from step_b200 import training
+    from step_b200.roi_layers import roi_align
+    gen = torch.Generator().manual_seed(3)
+    K, H, W, C = 8, 14, 14, 832
+    x = torch.randn(K, H, W, C, generator=gen).cuda()
+    tubes = synth.make_proposals(1, 11, 8, 224, 224)
+    import step_b200
+    flat, _ = step_b200.tube_utils.flatten_tubes(tubes, batch_idx=True)
+    rois = torch.from_numpy(flat).view(-1, 5).cuda()
+    y = roi_align(x.permute(0, 3, 1, 2), rois, (7, 7), 1.0 / 16.0, 0)          # channels-last fast path, fp32 exact
+    gy = torch.randn(y.shape, generator=gen).cuda()
+    gin = training.roi_align_backward_nhwc(gy.permute(0, 2, 3, 1).contiguous(), rois, 1.0 / 16.0, K, H, W, 0)
+    lhs = float((y.double() * gy.double()).sum())
+    rhs = float((x.double() * gin.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs))
+
+
+@pytest.mark.parametrize("shape", [(735, 256, 1024), (34496, 1024, 256), (5000, 64, 832), (100, 8, 16)])
+def test_conv1x1_wgrad_matches_matmul(shape):
+    from step_b200 import training
+    M, Cout, Cin = shape
+    gen = torch.Generator().manual_seed(M)
+    dz = (torch.randn(M, Cout, generator=gen) * 0.1).half().cuda()
+    x = torch.randn(M, Cin, generator=gen).half().cuda()
+    dw = training.conv1x1_wgrad(dz, x)
+    ref = dz.float().t() @ x.float()
+    assert float((dw - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+    assert torch.equal(dw, training.conv1x1_wgrad(dz, x))                       # fixed reduction order
+    dw2 = training.conv1x1_wgrad(dz, x, scale=0.5, out=dw.clone(), accumulate=True)
+    assert torch.allclose(dw2, 1.5 * dw, rtol=1e-6, atol=1e-6)
+
+
+def test_linear_backward_matches_matmul():
+    from step_b200 import training
+    gen = torch.Generator().manual_seed(9)
+    M, K, Nn = 24, 12544, 12
+    x = torch.randn(M, K, generator=gen).cuda()
+    w = (torch.randn(Nn, K, generator=gen) * 0.01).cuda()
+    dy = torch.randn(M, Nn, generator=gen).cuda()
+    dx, dw, db = training.linear_backward(x, w, dy)
+    assert torch.allclose(dx, dy @ w, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(dw, dy.t() @ x, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(db, dy.sum(0), rtol=1e-5, atol=1e-5)
+    dxh, dwh, _ = training.linear_backward(x.half(), w, dy)
+    assert torch.allclose(dwh, dy.t() @ x.half().float(), rtol=1e-3, atol=1e-3)
