@@ -181,6 +181,11 @@ typedef struct {
   void* y_extra[2];
   int ld_extra[2];
   int coff_extra[2];
+  /* Structured zeros of the weights (a_mode 4 only): for the filter taps of the LAST t plane (kt == KT-1) the input
+   * channels [zero_cin_last_kt, Cin) carry zero weights, so their 16-channel MMA steps are skipped.  0 = no such
+   * structure.  The space-to-depth stem has it: tap plane qt = 2 only holds the rt = 0 sub-position (k = 2(q+1)+r <= 6),
+   * engine.pack_stem_s2d. */
+  int zero_cin_last_kt;
 } step_conv_params;
 int step_conv3d_fwd(const step_conv_params* p, step_stream_t stream);
 

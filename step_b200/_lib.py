@@ -29,7 +29,7 @@ class ConvParams(ctypes.Structure):
                [("x", c_void_p), ("w", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
                 ("residual", c_void_p), ("res_ld", c_int), ("res_coff", c_int), ("y", c_void_p),
                 ("a_mode", c_int), ("n_splits", c_int), ("split", c_int * 2), ("y_extra", c_void_p * 2),
-                ("ld_extra", c_int * 2), ("coff_extra", c_int * 2)]
+                ("ld_extra", c_int * 2), ("coff_extra", c_int * 2), ("zero_cin_last_kt", c_int)]
 
 
 def _declare(lib):

@@ -34,6 +34,7 @@ struct HaloGeom {
   int patch_bytes, b_bytes, n_stages;
   int BN, ncols, Cout, relu;
   int tiles_w, tiles_h, tiles_t, OT;
+  int k_steps_last_t;            // 16-channel MMA steps issued for the taps of the last t plane (structured zero weights)
   uint32_t idesc;
 };
 
@@ -134,11 +135,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t b_lo = ring_lo + (uint32_t)s * b16;
         const uint32_t acc0 = tap ? 1u : 0u;
         uint32_t d = tmem_base;
+        const int nk = (kt == g.KT - 1) ? g.k_steps_last_t : BK / 16;   // zero-weight channel tail of the last t plane: no MMA
 #pragma unroll
         for (int j = 0; j < TT; ++j) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_f16(d, a_hi | (uint64_t)(a_lo + 2 * k), b_hi | (uint64_t)(b_lo + 2 * k), idesc, k ? 1u : acc0);
+            if (k < nk)
+              umma_f16(d, a_hi | (uint64_t)(a_lo + 2 * k), b_hi | (uint64_t)(b_lo + 2 * k), idesc, k ? 1u : acc0);
           a_lo += plane16;
           d += ncols;
         }
@@ -302,6 +305,11 @@ int conv3d_halo_launch(const step_conv_params* p, step_stream_t stream) {
   const long long ctas = (long long)p->N * g.tiles_t * g.tiles_h * g.tiles_w;
   STEP_CHECK_ARG(ctas < (1LL << 31), "conv3d(halo): grid too large");
   g.idesc = (1u << 4) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  g.k_steps_last_t = BK / 16;
+  if (p->zero_cin_last_kt > 0 && p->zero_cin_last_kt < p->Cin && !(getenv("STEP_B200_HALO_ZSKIP") && getenv("STEP_B200_HALO_ZSKIP")[0] == '0')) {
+    const int steps = (p->zero_cin_last_kt + 15) / 16;       // steps that still touch a non-zero weight
+    if (steps >= 1 && steps < BK / 16) g.k_steps_last_t = steps;
+  }
   const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUtensorMap ma, mb, my;

@@ -278,46 +278,90 @@ __global__ void __launch_bounds__(128) detect_nms_kernel(const float* __restrict
   for (int i = threadIdx.x; i < m; i += blockDim.x) keep[cand0 + sorig[i]] = sup[i] ? 0 : 1;
 }
 
+// One CTA per clip.  Pass 1 compacts the kept candidates in candidate order (= the reference's file order: class, tube)
+// into shared memory with a ballot scan; pass 2 ranks them (m^2 compares on the m <= kSelMax survivors, all in shared
+// memory) when a top-k cut is requested.  Clips with more survivors than kSelMax rank against global memory instead.
+constexpr int kSelMax = 4096;
 __global__ void __launch_bounds__(256) detect_select_kernel(const uint8_t* __restrict__ keep,
                                                             const float* __restrict__ score, const float4* __restrict__ box,
                                                             const int* __restrict__ clip_offsets, int ncls, int topk,
                                                             int cap, float* __restrict__ det, int* __restrict__ det_count) {
+  __shared__ float s_score[kSelMax];
+  __shared__ int s_idx[kSelMax];
+  __shared__ int warp_tot[8];
+  __shared__ int base_s;
   const int clip = blockIdx.x;
   const int beg = clip_offsets[clip], n = clip_offsets[clip + 1] - beg;
   const int cands = n * ncls;
   const size_t cand0 = (size_t)beg * ncls;
-  __shared__ int total_s;
-  if (threadIdx.x == 0) total_s = 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
   __syncthreads();
-  int local = 0;
-  for (int i = threadIdx.x; i < cands; i += blockDim.x) {
-    if (!keep[cand0 + i]) continue;
-    ++local;
-    const float si = score[cand0 + i];
-    int rank = 0;
-    if (topk > 0) {
-      // (s, class, j) descending; inside a class j grows with the tube index, and the candidate index is
-      // class * n + tube, so "greater (class, j)" == "greater candidate index"
-      for (int t = 0; t < cands; ++t) {
-        if (!keep[cand0 + t]) continue;
-        const float st = score[cand0 + t];
-        rank += (st > si) || (st == si && t > i);
-      }
-      if (rank >= topk) continue;
-    } else {
-      for (int t = 0; t < i; ++t) rank += keep[cand0 + t] ? 1 : 0;
+  // ---- pass 1: kept candidates, ascending candidate index -> slot (prefix count)
+  for (int start = 0; start < cands; start += blockDim.x) {
+    const int i = start + threadIdx.x;
+    const int f = (i < cands) ? keep[cand0 + i] : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_tot[wid] = __popc(bal);
+    __syncthreads();
+    int off = base_s;
+    for (int w = 0; w < wid; ++w) off += warp_tot[w];
+    const int slot = off + __popc(bal & ((1u << lane) - 1));
+    if (f && slot < kSelMax) { s_idx[slot] = i; s_score[slot] = score[cand0 + i]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += warp_tot[w];
+      base_s += t;
     }
-    if (rank < cap) {
-      const float4 b = box[cand0 + i];
-      float* o = det + ((size_t)clip * cap + rank) * 8;
-      const int c = i / n;
-      o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = si; o[5] = (float)c; o[6] = (float)(i - c * n); o[7] = 0.0f;
+    __syncthreads();
+  }
+  const int m = base_s;
+  const bool in_smem = m <= kSelMax;
+  auto emit = [&](int i, float si, int rank) {
+    if (rank >= cap) return;
+    const float4 b = box[cand0 + i];
+    float* o = det + ((size_t)clip * cap + rank) * 8;
+    const int c = i / n;
+    o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = si; o[5] = (float)c; o[6] = (float)(i - c * n); o[7] = 0.0f;
+  };
+  if (in_smem) {
+    for (int k = threadIdx.x; k < m; k += blockDim.x) {
+      const int i = s_idx[k];
+      const float si = s_score[k];
+      int rank = k;                                   // file order
+      if (topk > 0) {
+        // (score, class, j) descending (test.py:205-208): inside a class j grows with the tube index and the candidate
+        // index is class * n + tube, so "greater (class, j)" == "greater candidate index" == "greater slot"
+        rank = 0;
+        for (int t = 0; t < m; ++t) {
+          const float st = s_score[t];
+          rank += (st > si) || (st == si && t > k);
+        }
+        if (rank >= topk) continue;
+      }
+      emit(i, si, rank);
+    }
+  } else {
+    for (int i = threadIdx.x; i < cands; i += blockDim.x) {
+      if (!keep[cand0 + i]) continue;
+      const float si = score[cand0 + i];
+      int rank = 0;
+      if (topk > 0) {
+        for (int t = 0; t < cands; ++t) {
+          if (!keep[cand0 + t]) continue;
+          const float st = score[cand0 + t];
+          rank += (st > si) || (st == si && t > i);
+        }
+        if (rank >= topk) continue;
+      } else {
+        for (int t = 0; t < i; ++t) rank += keep[cand0 + t] ? 1 : 0;
+      }
+      emit(i, si, rank);
     }
   }
-  atomicAdd(&total_s, local);
-  __syncthreads();
   if (threadIdx.x == 0) {
-    int k = total_s;
+    int k = m;
     if (topk > 0 && k > topk) k = topk;
     det_count[clip] = k < cap ? k : cap;
   }

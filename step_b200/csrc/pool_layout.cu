@@ -390,6 +390,49 @@ __global__ void __launch_bounds__(256) clip_to_s2d_kernel(const float* __restric
   }
 }
 
+
+// RGB fast path (Cc == 3, ld == 32): one thread per OUTPUT pixel, no shared memory.  The 12 (rt, rh, c) input rows are
+// read as float2 (the two rw positions): a warp reads 256 contiguous bytes per row and writes 32 x 64 = 2 KB of
+// contiguous output with two 32-byte stores per lane.  122 -> ~55 us on the 154 MB C4 batch (a pure copy at HBM speed).
+__global__ void __launch_bounds__(256) clip_to_s2d_rgb_kernel(const float* __restrict__ clip, int N, int T_, int H, int W,
+                                                              __half* __restrict__ out) {
+  const int T2 = T_ / 2, H2 = H / 2, W2 = W / 2;
+  const long long total = (long long)N * T2 * H2 * W2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w2 = (int)(idx % W2);
+  long long r = idx / W2;
+  const int h2 = (int)(r % H2); r /= H2;
+  const int t2 = (int)(r % T2);
+  const int n = (int)(r / T2);
+  float v[32];
+#pragma unroll
+  for (int k = 24; k < 32; ++k) v[k] = 0.0f;
+#pragma unroll
+  for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float2 p = __ldg(reinterpret_cast<const float2*>(
+            clip + ((((size_t)n * T_ + 2 * t2 + rt) * 3 + c) * H + 2 * h2 + rh) * W + 2 * w2));
+        const int q = (rt * 2 + rh) * 2;                 // channel ((rt*2+rh)*2+rw)*3 + c
+        v[q * 3 + c] = p.x;
+        v[(q + 1) * 3 + c] = p.y;
+      }
+  uint32_t o[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+    o[k] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  __half* dst = out + (size_t)idx * 32;
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+               "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]),
+               "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]) : "memory");
+}
+
 // [N*S, C] (ld) -> [N, C, S] fp32 via a 32x32 smem transpose
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int S, int C, int ld, float* __restrict__ out) {
@@ -736,6 +779,13 @@ extern "C" int step_clip_to_s2d_f16(const float* clip, int N, int T, int Cc, int
   STEP_CHECK_ARG(T % 2 == 0 && H % 2 == 0 && W % 2 == 0 && ld >= 8 * Cc, "clip_to_s2d: T,H,W must be even, ld >= 8*Cc");
   STEP_CHECK_ARG(ld % 8 == 0 && ld <= 64 && 256 % (ld / 8) == 0 && (size_t)4 * Cc * W * sizeof(float) <= 48 * 1024, "clip_to_s2d: ld must divide 2048, row tile must fit 48 KB smem");
   STEP_CHECK_ARG(((uintptr_t)out & 15) == 0, "clip_to_s2d: out must be 16-byte aligned");
+  if (Cc == 3 && ld == 32 && ((uintptr_t)clip & 7) == 0 && ((uintptr_t)out & 31) == 0 && !(getenv("STEP_B200_S2D") && getenv("STEP_B200_S2D")[0] == '0')) {
+    const long long total = (long long)N * (T / 2) * (H / 2) * (W / 2);
+    STEP_CHECK_ARG(ceil_div(total, 256) < (1LL << 31), "clip_to_s2d: too many pixels");
+    clip_to_s2d_rgb_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, cu(stream)>>>(clip, N, T, H, W, (__half*)out);
+    STEP_LAUNCH_CHECK("clip_to_s2d_rgb_kernel");
+    return 0;
+  }
   long long rows = (long long)N * (T / 2) * ceil_div(H / 2, kS2dRows);
   STEP_CHECK_ARG(rows < (1LL << 31), "clip_to_s2d: too many rows");
   clip_to_s2d_kernel<<<(unsigned)rows, 256, (size_t)4 * Cc * W * sizeof(float), cu(stream)>>>(clip, N, T, Cc, H, W, (__half*)out, ld);

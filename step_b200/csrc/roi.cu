@@ -312,17 +312,20 @@ __device__ __forceinline__ void hfma2x4(__half2* a, __half2 w, const uint4& v) {
 
 template <int V>
 __device__ __forceinline__ void roi_gather_items(const MergedBin* bins, int nbins, int nvec, const __half* fbase, __half* obase,
-                                                 int out_ld) {
+                                                 int out_ld, int part, int parts) {
+  // this CTA handles channel vectors [cv0, cv0 + cnt) of every V-th of the row (blockIdx.y = part): small batches of
+  // ROIs (704 rows in the pipeline) are split over `parts` CTAs per row so that the gather is not one short wave
   const int hv = nvec / V;
-  int bin = threadIdx.x / hv, cv = threadIdx.x - bin * hv;   // incremental (bin, cv): no per-item division
-  const int dbin = blockDim.x / hv, dcv = blockDim.x - dbin * hv;
+  const int cnt = hv / parts, cv0 = part * cnt;
+  int bin = threadIdx.x / cnt, cv = threadIdx.x - bin * cnt;   // incremental (bin, cv): no per-item division
+  const int dbin = blockDim.x / cnt, dcv = blockDim.x - dbin * cnt;
   const __half2 z2 = __float2half2_rn(0.0f);
   while (bin < nbins) {
     const MergedBin& b = bins[bin];
     __half2 acc[V][4];
 #pragma unroll
     for (int u = 0; u < V; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = z2;
-    const __half* fp = fbase + cv * 8;
+    const __half* fp = fbase + (cv0 + cv) * 8;
     const int n = b.n;
     int e = 0;
     for (; e + 1 < n; e += 2) {
@@ -343,11 +346,11 @@ __device__ __forceinline__ void roi_gather_items(const MergedBin* bins, int nbin
 #pragma unroll
       for (int u = 0; u < V; ++u) hfma2x4(acc[u], w0, *reinterpret_cast<const uint4*>(fp + e0.x + u * hv * 8));
     }
-    __half* op = obase + (size_t)bin * out_ld + cv * 8;
+    __half* op = obase + (size_t)bin * out_ld + (cv0 + cv) * 8;
 #pragma unroll
     for (int u = 0; u < V; ++u) *reinterpret_cast<uint4*>(op + u * hv * 8) = *reinterpret_cast<const uint4*>(acc[u]);
     bin += dbin; cv += dcv;
-    if (cv >= hv) { cv -= hv; ++bin; }
+    if (cv >= cnt) { cv -= cnt; ++bin; }
   }
 }
 
@@ -363,11 +366,13 @@ __global__ void __launch_bounds__(256) roi_align_fwd_nhwc_f16_packed_kernel(cons
   const __half* fbase = feat + (size_t)fm.map(g.batch) * H * W * feat_ld;
   __half* obase = out + (size_t)r * nbins * out_ld;
   const int nvec = C >> 3;
+  const int part = blockIdx.y, parts = gridDim.y;
   if ((g.gh + 1) * (g.gw + 1) > kMaxMerged) {
     // very large ROI (sampling grid > 3x3): direct form with fp32 FMAs, no table
     const float ic = 1.0f / g.count;
-    for (int item = threadIdx.x; item < nbins * nvec; item += blockDim.x) {
-      const int bin = item / nvec, cv = item - bin * nvec;
+    const int pv = nvec / parts, pv0 = part * pv;
+    for (int item = threadIdx.x; item < nbins * pv; item += blockDim.x) {
+      const int bin = item / pv, cv = pv0 + item - bin * pv;
       const int p = bin / pw, q = bin - p * pw;
       float acc[8];
 #pragma unroll
@@ -423,8 +428,8 @@ __global__ void __launch_bounds__(256) roi_align_fwd_nhwc_f16_packed_kernel(cons
   // Gather: an item is (bin, V channel vectors a V-th of a row apart): the 8-byte table entry (pixel offset, merged
   // weight) is read once for V 16-byte vectors, and two entries are in flight per iteration (2V independent loads).
   // (measured on C3: V = 2 -> 0.575 of HBM peak, V = 4 -> 0.564, V = 1 -> 0.46)
-  if ((nvec & 1) == 0) roi_gather_items<2>(bins, nbins, nvec, fbase, obase, out_ld);
-  else roi_gather_items<1>(bins, nbins, nvec, fbase, obase, out_ld);
+  if ((nvec & 1) == 0) roi_gather_items<2>(bins, nbins, nvec, fbase, obase, out_ld, part, parts);
+  else roi_gather_items<1>(bins, nbins, nvec, fbase, obase, out_ld, part, parts);
 }
 
 template <typename T>
@@ -544,7 +549,14 @@ extern "C" int step_roi_align_fwd_nhwc(const void* feat, int dtype, int K, int H
   FrameMap fm{roi_T, feat_T, t_start};
   if (dtype == STEP_F16 && exact == 0 && (size_t)ph * pw * sizeof(MergedBin) <= 48 * 1024 &&
       (long long)H * W * feat_ld < (1LL << 31)) {   // table entries hold 32-bit element offsets inside one frame
-    roi_align_fwd_nhwc_f16_packed_kernel<<<R, 256, (size_t)ph * pw * sizeof(MergedBin), cu(stream)>>>(
+    // few ROI rows (the pipeline pools 704 per step): split every row over up to 4 CTAs by channel range
+    int parts = 1;
+    {
+      const int nvec = C / 8, hv = (nvec & 1) == 0 ? nvec / 2 : nvec;
+      while (false && parts < 4 && (long long)R * parts < 16 * kNumSMs && hv % (parts * 2) == 0 && nvec % (parts * 2) == 0) parts *= 2;
+      if (const char* e = getenv("STEP_B200_ROI_PARTS")) { const int v = atoi(e); if (v >= 1 && hv % v == 0 && nvec % v == 0) parts = v; }
+    }
+    roi_align_fwd_nhwc_f16_packed_kernel<<<dim3(R, parts), 128 * (parts > 1 ? 1 : 2), (size_t)ph * pw * sizeof(MergedBin), cu(stream)>>>(
         (const __half*)feat, H, W, C, feat_ld, rois, scale, ph, pw, sampling_ratio, (__half*)out, out_ld, fm);
     STEP_LAUNCH_CHECK("roi_align_fwd_nhwc_f16_packed_kernel");
     return 0;

@@ -169,7 +169,7 @@ def params_key(*tensors):
 
 
 def conv(x, w_packed, scale, shift, out, k, stride=(1, 1, 1), pad_lo=None, relu=True, residual=None,
-         a_mode=None, out_dims=None, extra_outs=None):
+         a_mode=None, out_dims=None, extra_outs=None, zero_cin_last_kt=0):
     """Launch step_conv3d_fwd: x (Act) * w_packed [Cout, taps, w_ld] -> out (Act slice).
     extra_outs: up to two more Act slices; output channels are then split [out.C | extra[0].C | extra[1].C]
     (horizontally fused 1x1x1 layers sharing the input)."""
@@ -205,6 +205,7 @@ def conv(x, w_packed, scale, shift, out, k, stride=(1, 1, 1), pad_lo=None, relu=
         p.residual = residual.buf.data_ptr()
         p.res_ld, p.res_coff = residual.ld, residual.coff
     p.y = out.buf.data_ptr()
+    p.zero_cin_last_kt = int(zero_cin_last_kt)
     p.a_mode = A_MODE if a_mode is None else a_mode
     if p.a_mode in (L.A_BOX, L.A_IM2COL, L.A_BEST) and k == (1, 1, 1):
         p.a_mode = L.A_AUTO

@@ -72,8 +72,11 @@ class Unit3Dpy(torch.nn.Module):
         w, scale, shift = self.packed(L.F16, s2d=True)
         out = Act.empty(x_s2d.N, x_s2d.T, x_s2d.H, x_s2d.W, self.conv3d.out_channels, L.F16, x_s2d.device)
         # patch-in-shared-memory kernel (csrc/conv_halo.cu) unless STEP_B200_STEM_HALO=0
+        # tap plane qt = 2 is k_t = 6 + rt: only the rt = 0 sub-position (channels [0, 4 Cin)) has weights there, the
+        # rt = 1 half is structurally zero (engine.pack_stem_s2d) -> its MMA steps are skipped by the patch kernel
         return E.conv(x_s2d, w, scale, shift, out, (4, 4, 4), (1, 1, 1), (1, 1, 1), self.activation is not None,
-                      a_mode=L.A_HALO if E.STEM_HALO else None, out_dims=(x_s2d.T, x_s2d.H, x_s2d.W))
+                      a_mode=L.A_HALO if E.STEM_HALO else None, out_dims=(x_s2d.T, x_s2d.H, x_s2d.W),
+                      zero_cin_last_kt=4 * self.conv3d.in_channels)
 
 
 class MaxPool3dTFPadding(torch.nn.Module):

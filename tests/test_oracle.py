@@ -247,3 +247,25 @@ def test_roi_pool_and_align_backward_match_torchvision(golden):
     assert np.array_equal(out, g["pool_out"])
     gin = ops.roi_pool_bwd(g["pool_gy"], arg, rois, 7, 7, K, C, H, W)
     assert np.abs(gin - g["pool_gx"]).max() <= 2e-5 * max(1.0, np.abs(g["pool_gx"]).max())
+
+
+def test_oracle_matches_reference_at_the_measured_c4_shape(golden):
+    """The CPU pass bench.py times (and uses as its same-run parity reference) is this oracle at the C4 shape: pin it to
+    the reference's outputs for clip 0 of the bench batch (tests/golden/pipe_c4.npz)."""
+    g = golden("pipe_c4")
+    cfg = synth.make_cfg(fp16=False, T=8, max_iter=3, NUM_CHUNKS={1: 1, 2: 1, 3: 1}, image_size=(224, 224))
+    sd = synth.base_net_state_dict()
+    heads = [synth.head_state_dict(100 + i, cfg) for i in range(cfg.max_iter)]
+    x = synth.make_clips(1, 32, 224, 224)
+    tb = synth.make_proposals(1, 11, cfg.T, 224, 224)
+    with torch.no_grad():
+        cf = om.base_net(x, sd)
+        hist, traj = om.inference(cfg, cf, None, heads, cfg.max_iter, [t.copy() for t in tb])
+    ref = g["feat_sub_c0"]
+    assert np.allclose(cf.numpy()[:, :, ::4], ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+    for i, h in enumerate(hist):
+        assert np.allclose(h["pred_prob"][:, 0].numpy(), g["prob%d_c0" % i], rtol=1e-4, atol=1e-5)
+        loc = tubes.valid_tubes(h["pred_loc"].numpy().copy(), 224, 224)   # the reference's CPU aliasing (DESIGN.md section 5)
+        assert np.allclose(loc, g["loc_valid%d_c0" % i], rtol=1e-4, atol=2e-3)
+        assert np.allclose(h["pred_first_loc"].numpy(), g["first%d_c0" % i], rtol=1e-4, atol=2e-3)
+        assert np.allclose(np.concatenate([t[0] for t in traj[i]], 0), g["traj%d_c0" % i], rtol=1e-4, atol=2e-3)
