@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(256) roi_align_fwd_nhwc_kernel(const T* __rest
   }
 }
 
+
 // fp16 "packed" fast path.  Two observations from the C3 profile (profiles/): the direct form is bound by
 // instruction issue and by the L1 data path (4 taps x g^2 samples = ~10 sixteen-byte loads per 16-byte output).
 //  (1) the g^2 samples of a bin hit only <= (g+1)^2 distinct pixels: their bilinear weights are merged per

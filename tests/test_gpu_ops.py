@@ -277,3 +277,50 @@ def test_roi_pool_and_align_backward_match_torchvision(golden):
     assert np.array_equal(y.detach().cpu().numpy(), g["pool_out"])
     y.backward(cu(g["pool_gy"]))
     assert np.abs(x.grad.cpu().numpy() - g["pool_gx"]).max() <= 2e-5 * max(1.0, np.abs(g["pool_gx"]).max())
+
+
+def test_roi_align_c3_80000_rows_bit_exact():
+    """BASELINE.json configs[2] (C3) at full size: 10 000 tubes x T' = 8 = 80 000 ROI rows over a [64,14,14,832] map,
+    the exact channels-last kernels.  512 sampled rows are compared bit for bit with the C restatement of
+    cpu/ROIAlign_cpu.cpp:137-243 (oracle/step_oracle.c, itself pinned to the reference's compiled op): fp32 exactly, fp16
+    == round_to_half(exact fp32 on the half inputs).  Plus a size-independent property on ALL rows: pooling a constant
+    map returns the constant wherever no sample falls outside the map."""
+    from step_b200 import synth, _lib as L
+    rois_np, _, _ = synth.make_c3_rois()
+    R = rois_np.shape[0]
+    assert R == 80000
+    rois = cu(rois_np)
+    g = torch.Generator().manual_seed(1234)
+    feat32 = torch.randn(64, 14, 14, 832, generator=g).cuda()
+    idx = np.random.RandomState(0).choice(R, 512, replace=False)
+    for code, feat in ((L.F32, feat32), (L.F16, feat32.half())):
+        o = torch.empty((R, 7, 7, 832), dtype=feat.dtype, device="cuda")
+        L.check(L.lib().step_roi_align_fwd_nhwc(L.ptr(feat), code, 64, 14, 14, 832, 832, L.ptr(rois), R, 1 / 16., 7, 7, 0,
+                                                L.ptr(o), 832, 0, 0, 0, 1, L.stream()))
+        ref = oops.roi_align_fwd(feat.float().cpu().numpy().transpose(0, 3, 1, 2), rois_np[idx], 1 / 16., 7, 7, 0)
+        got = o[torch.from_numpy(idx).cuda()].float().cpu().numpy().transpose(0, 3, 1, 2)
+        refq = ref if code == L.F32 else ref.astype(np.float16).astype(np.float32)
+        assert np.array_equal(got, refq)
+        del o
+    ones = torch.ones(64, 14, 14, 8, device="cuda")
+    o = torch.empty((R, 7, 7, 8), dtype=torch.float32, device="cuda")
+    L.check(L.lib().step_roi_align_fwd_nhwc(L.ptr(ones), L.F32, 64, 14, 14, 8, 8, L.ptr(rois), R, 1 / 16., 7, 7, 0,
+                                            L.ptr(o), 8, 0, 0, 0, 1, L.stream()))
+    assert float(o.min()) > 0.0 and float(o.max()) <= 1.0 + 1e-6
+    inside = (rois_np[:, 1] >= 0) & (rois_np[:, 2] >= 0) & (rois_np[:, 3] <= 223) & (rois_np[:, 4] <= 223)
+    assert float((o[torch.from_numpy(inside).cuda()] - 1.0).abs().max()) <= 1e-6
+
+
+def test_roi_align_exact_huge_roi_uncached_grid():
+    """ROIs far larger than the map (adaptive sampling grid > 4 x 4: the per-ROI tap table does not fit shared memory and
+    the taps are recomputed per use) stay bit-exact, for 7 x 7 and for other output sizes."""
+    from step_b200.roi_layers import roi_align
+    rs = np.random.RandomState(8)
+    K, C, H, W = 2, 16, 14, 14
+    feat = rs.randn(K, C, H, W).astype(np.float32)
+    rois = np.array([[0, -500, -300, 3000, 2500], [1, 0, 0, 1600, 223], [1, 10, 10, 900, 1200], [0, 3, 3, 100, 100]], np.float32)
+    f_cl = cu(feat).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    for out_size in ((7, 7), (3, 5)):
+        ref = oops.roi_align_fwd(feat, rois, 1 / 16., out_size[0], out_size[1], 0)
+        out = roi_align(f_cl, cu(rois), out_size, 1 / 16., 0)
+        assert np.array_equal(out.cpu().numpy(), ref)
