@@ -6,6 +6,7 @@
 #include <atomic>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/step_b200.h"
 
@@ -33,6 +34,13 @@ inline cudaStream_t cu(step_stream_t s) { return reinterpret_cast<cudaStream_t>(
       return step::fail((int)e__, "%s: %s", name, cudaGetErrorString(e__));        \
     }                                                                               \
   } while (0)
+
+// STEP_B200_PDL=0 launches the conv kernels without programmatic dependent launch (A/B timing)
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("STEP_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -99,6 +99,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();                 // the producer of x (the previous kernel in the stream) has finished
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== producer =====================
@@ -226,7 +228,16 @@ static int launch_halo_tt(const CUtensorMap& ma, const CUtensorMap& mb, const CU
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BK, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemMax);
     if (e != cudaSuccess) return fail((int)e, "conv_halo_kernel attribute: %s", cudaGetErrorString(e));
   }
-  conv_halo_kernel<BK, TT><<<grid, kHaloThreads, smem, s>>>(ma, mb, my, g, p->scale, p->shift);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kHaloThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<BK, TT>, ma, mb, my, g, p->scale, p->shift);
+  if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "conv_halo_kernel launch: %s", cudaGetErrorString(le)); }
   STEP_LAUNCH_CHECK("conv_halo_kernel");
   return 0;
 }

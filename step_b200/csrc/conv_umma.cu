@@ -120,6 +120,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();                 // the producer of x (the previous kernel in the stream) has finished
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -455,6 +457,8 @@ conv_umma_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   if (two) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();                    // the producer of x / residual (the previous kernel in the stream) has finished
+  pdl_launch_dependents();
 
   // tile -> (m tile, n offset).  In a cluster the two CTAs take M tiles 2*pm and 2*pm+1 of the same N tile (the odd
   // one may lie past the end: its loads are zero-filled and nothing is stored, but it still runs the k loop).
@@ -1184,8 +1188,17 @@ static int launch_bk(const ConvPlan& pl, const step_conv_params* p, cudaStream_t
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BK, kHasRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return fail((int)e, "conv3d(f16): smem attribute: %s", cudaGetErrorString(e));
   }
-  conv_umma_kernel<BK, kHasRes><<<pl.grid, kThreads, pl.smem_bytes, s>>>(pl.map_a, pl.map_b, pl.g, p->scale, p->shift,
-                                                                        (const __half*)p->residual, (__half*)p->y);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = pl.grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = pl.smem_bytes; cfg.stream = s;
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_umma_kernel<BK, kHasRes>, pl.map_a, pl.map_b, pl.g, p->scale, p->shift,
+                                      (const __half*)p->residual, (__half*)p->y);
+  if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, "conv_umma_kernel launch: %s", cudaGetErrorString(le)); }
   STEP_LAUNCH_CHECK("conv_umma_kernel");
   return 0;
 }
@@ -1199,16 +1212,23 @@ static int launch_persist(const ConvPlan& pl, const step_conv_params* p, cudaStr
   }
   const int total = pl.persist_tiles;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (pl.g.cluster == 2 || kPair) {
     const int pairs = total < kNumSMs / 2 ? total : kNumSMs / 2;
     cfg.gridDim = dim3(2 * pairs);
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
   } else {
     cfg.gridDim = dim3(total < kNumSMs ? total : kNumSMs);
   }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
   cfg.blockDim = dim3(kThreadsP);
   cfg.dynamicSmemBytes = pl.persist_smem;
   cfg.stream = s;

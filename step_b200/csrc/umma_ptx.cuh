@@ -95,6 +95,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization): a kernel launched with the attribute
+// may start while its predecessor in the stream is still running; everything up to pdl_wait() (barrier init, TMEM
+// allocation, descriptor prefetch, constant loads) overlaps the predecessor's tail.  pdl_wait() returns once the
+// predecessor grid has completed and its writes are visible; pdl_launch_dependents() lets the NEXT kernel start early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
