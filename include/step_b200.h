@@ -245,6 +245,28 @@ size_t step_conv1x1_wgrad_workspace_bytes(int M, int Cout, int Cin);
 int step_conv1x1_wgrad_f16(const void* dz, int dz_ld, const void* x, int x_ld, int M, int Cout, int Cin, float scale,
                            float* dw, int dw_ld, int accumulate, void* workspace, size_t ws_bytes, step_stream_t stream);
 
+/* Weight gradient of a stride-1 convolution with KT x KH x KW taps and low padding (PT, PH, PW) (zero outside the map):
+ * dw[Cout, taps, dw_ld >= Cin] (+)= scale * sum_m dz[m, co] x[shift_tap(m), ci], x and dz on the same [N,T,H,W] pixel grid. */
+size_t step_conv_wgrad_workspace_bytes(int M, int Cout, int Cin, int taps);
+int step_conv_wgrad_f16(const void* dz, int dz_ld, const void* x, int x_ld, int N, int T, int H, int W, int Cout, int Cin,
+                        int KT, int KH, int KW, int PT, int PH, int PW, float scale, float* dw, int dw_ld, int accumulate,
+                        void* workspace, size_t ws_bytes, step_stream_t stream);
+/* y = relu(scale * conv + shift (+ residual)): dz = dy * [y > 0] * scale (dense [M, C] at dz_ld), and, when dres is given,
+ * dres += dy * [y > 0] (the residual input's gradient, accumulated in place).  fp16, channel slices via the ld arguments. */
+int step_act_bwd_f16(const void* dy, int dy_ld, const void* y, int y_ld, const float* scale, int relu, long long M, int C,
+                     void* dz, int dz_ld, void* dres, int dres_ld, step_stream_t stream);
+/* out[c] = scale * sum_m x[m, c] (bias gradients); workspace >= 64 * C floats; fixed summation order. */
+int step_colsum_f16(const void* x, int ld, long long M, int C, float scale, float* out, float* workspace, step_stream_t stream);
+/* Backward of step_mean_mid: dx[a, b, p, c] += gscale * g[a, p*C + c] / B (fp16 dx, channel stride ld). */
+int step_mean_mid_bwd(const float* g, int A, int B, int P, int C, float gscale, void* dx, int ld, step_stream_t stream);
+/* dst[m, c] (fp16, channel stride ld) += gscale * src[m, c] (fp32 [M, C]). */
+int step_f32_accum_f16(const float* src, long long M, int C, float gscale, void* dst, int ld, step_stream_t stream);
+/* Backward of step_maxpool3d_fwd (zero padding takes part in the maximum, first maximum in scan order wins as in ATen):
+ * dx += scatter(dy) without atomics; argmax_ws: N*OT*OH*OW*C bytes of scratch. */
+int step_maxpool3d_bwd_f16(const void* x, int x_ld, const void* dy, int dy_ld, int N, int T, int H, int W, int C, int KT,
+                           int KH, int KW, int ST, int SH, int SW, int PT, int PH, int PW, int pad_hi_t, int pad_hi_h,
+                           int pad_hi_w, int OT, int OH, int OW, void* dx, int dx_ld, uint8_t* argmax_ws, step_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

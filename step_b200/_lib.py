@@ -70,6 +70,13 @@ def _declare(lib):
         "step_linear_small_n_bwd": ([P, I, I, I, I, P, P, I, P, I, P, P, S], c_int),
         "step_conv1x1_wgrad_workspace_bytes": ([I, I, I], c_size_t),
         "step_conv1x1_wgrad_f16": ([P, I, P, I, I, I, I, Fl, P, I, I, P, c_size_t, S], c_int),
+        "step_conv_wgrad_workspace_bytes": ([I, I, I, I], c_size_t),
+        "step_conv_wgrad_f16": ([P, I, P, I, I, I, I, I, I, I, I, I, I, I, I, I, Fl, P, I, I, P, c_size_t, S], c_int),
+        "step_act_bwd_f16": ([P, I, P, I, P, I, ctypes.c_longlong, I, P, I, P, I, S], c_int),
+        "step_colsum_f16": ([P, I, ctypes.c_longlong, I, Fl, P, P, S], c_int),
+        "step_mean_mid_bwd": ([P, I, I, I, I, Fl, P, I, S], c_int),
+        "step_f32_accum_f16": ([P, ctypes.c_longlong, I, Fl, P, I, S], c_int),
+        "step_maxpool3d_bwd_f16": ([P, I, P, I] + [I] * 20 + [P, I, P, S], c_int),
         "step_debug_tma_tile": ([ctypes.POINTER(ConvParams), I, I, I, I, I, P, P, P, S], c_int),
     }
     for name, (argtypes, restype) in sigs.items():

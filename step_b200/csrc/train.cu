@@ -291,6 +291,159 @@ __global__ void __launch_bounds__(256) linear_bwd_dx_kernel(const float* __restr
   dx[i] = acc;
 }
 
+
+// ---- elementwise pieces of the conv backward ---------------------------------------------------------------------------
+// y = relu(scale * conv + shift (+ residual))  (Unit3Dpy, i3dpt.py:103-111; Bottleneck, two_branch.py:60-111):
+//   dz = dy * [y > 0] * scale      gradient w.r.t. the raw convolution output (operand of dgrad / wgrad)
+//   dres += dy * [y > 0]           gradient flowing into the residual input, accumulated in place
+// dy / y / dres are channel slices of wider fp16 buffers (ld, coff); dz is dense [M, C] at dz_ld / dz_coff.
+__global__ void __launch_bounds__(256) act_bwd_kernel(const __half* __restrict__ dy, int dy_ld, const __half* __restrict__ y,
+                                                      int y_ld, const float* __restrict__ scale, int relu, long long M, int C,
+                                                      __half* __restrict__ dz, int dz_ld, __half* __restrict__ dres,
+                                                      int dres_ld) {
+  const int cv = C >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * cv) return;
+  const long long m = i / cv;
+  const int c = (int)(i - m * cv) * 8;
+  float g[8], v[8];
+  load16(dy + (size_t)m * dy_ld + c, g);
+  if (relu) {
+    load16(y + (size_t)m * y_ld + c, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = v[k] > 0.0f ? g[k] : 0.0f;
+  }
+  if (dres) {
+    float r[8];
+    load16(dres + (size_t)m * dres_ld + c, r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] += g[k];
+    store16(dres + (size_t)m * dres_ld + c, r);
+  }
+  if (scale) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] *= scale[c + k];
+  }
+  store16(dz + (size_t)m * dz_ld + c, g);
+}
+
+// column sums of a [M, C] fp16 matrix in fp32 (bias gradients), fixed order: thread per column block, rows ascending in
+// chunks that a second pass adds in chunk order
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const __half* __restrict__ x, int ld, long long M, int C, int rows_per,
+                                                             float* __restrict__ partial) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long m0 = (long long)blockIdx.y * rows_per, m1 = m0 + rows_per < M ? m0 + rows_per : M;
+  float acc = 0.0f;
+  for (long long m = m0; m < m1; ++m) acc += __half2float(x[(size_t)m * ld + c]);
+  partial[(size_t)blockIdx.y * C + c] = acc;
+}
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, int chunks, int C, float scale,
+                                                            float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.0f;
+  for (int k = 0; k < chunks; ++k) acc += partial[(size_t)k * C + c];
+  out[c] = acc * scale;
+}
+
+// temporal-mean backward (two_branch.py:249: the class scores are averaged over T'):  dx[a][b][p][c] += g[a][p*C + c] / B
+__global__ void __launch_bounds__(256) mean_mid_bwd_kernel(const float* __restrict__ g, int A, int B, int P, int C, float gscale,
+                                                           __half* __restrict__ dx, int ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)A * B * P * C) return;
+  const int c = (int)(i % C);
+  long long r = i / C;
+  const int p = (int)(r % P); r /= P;
+  const int b = (int)(r % B);
+  const int a = (int)(r / B);
+  __half* d = dx + ((((size_t)a * B + b) * P + p) * ld + c);
+  *d = __float2half_rn(__half2float(*d) + g[(size_t)a * P * C + (size_t)p * C + c] * gscale / (float)B);
+}
+
+// fp32 [M, C] (scaled) accumulated into an fp16 channel slice
+__global__ void __launch_bounds__(256) f32_accum_f16_kernel(const float* __restrict__ src, long long M, int C, float gscale,
+                                                            __half* __restrict__ dst, int ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C) return;
+  const long long m = i / C;
+  const int c = (int)(i - m * C);
+  __half* d = dst + (size_t)m * ld + c;
+  *d = __float2half_rn(__half2float(*d) + src[i] * gscale);
+}
+
+// ---- max-pool backward (MaxPool3dTFPadding, i3dpt.py:114-126: zero ConstantPad3d, then MaxPool3d) ---------------------------
+// Pass 1 (per output): which tap of the window holds the maximum -- first maximum in (kt, kh, kw) scan order with '>' like
+// ATen's max_pool3d_with_indices; a padded position holds the value 0 and takes part (its gradient is dropped).
+// Pass 2 (per input): gather dy from the windows whose recorded tap points at this input.  No atomics.
+struct PoolGeom { int N, T, H, W, C, KT, KH, KW, ST, SH, SW, PT, PH, PW, OT, OH, OW, QT, QH, QW; };   // Q*: high-side zero padding
+
+__global__ void __launch_bounds__(256) maxpool_argmax_kernel(PoolGeom g, const __half* __restrict__ x, int x_ld,
+                                                             uint8_t* __restrict__ arg) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)g.N * g.OT * g.OH * g.OW * g.C;
+  if (i >= total) return;
+  const int c = (int)(i % g.C);
+  long long r = i / g.C;
+  const int ow = (int)(r % g.OW); r /= g.OW;
+  const int oh = (int)(r % g.OH); r /= g.OH;
+  const int ot = (int)(r % g.OT);
+  const int n = (int)(r / g.OT);
+  float best = 0.0f;
+  int bi = -1, tap = 0;
+  for (int kt = 0; kt < g.KT; ++kt)
+    for (int kh = 0; kh < g.KH; ++kh)
+      for (int kw = 0; kw < g.KW; ++kw, ++tap) {
+        const int t = ot * g.ST + kt - g.PT, h = oh * g.SH + kh - g.PH, w = ow * g.SW + kw - g.PW;
+        // positions beyond the padded extent do not exist (ceil_mode overhang); inside the pad the value is 0
+        const bool in_t = t >= 0 && t < g.T, in_h = h >= 0 && h < g.H, in_w = w >= 0 && w < g.W;
+        const bool pad_t = t < 0 || (t >= g.T && t < g.T + g.QT), pad_h = h < 0 || (h >= g.H && h < g.H + g.QH),
+                   pad_w = w < 0 || (w >= g.W && w < g.W + g.QW);
+        if (!((in_t || pad_t) && (in_h || pad_h) && (in_w || pad_w))) continue;
+        const bool real = in_t && in_h && in_w;
+        const float v = real ? __half2float(x[((((size_t)n * g.T + t) * g.H + h) * g.W + w) * x_ld + c]) : 0.0f;
+        if (bi < 0 || v > best) { best = v; bi = real ? tap : 254; }
+      }
+  arg[i] = (uint8_t)(bi < 0 ? 255 : bi);
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(PoolGeom g, const __half* __restrict__ dy, int dy_ld,
+                                                          const uint8_t* __restrict__ arg, __half* __restrict__ dx, int dx_ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)g.N * g.T * g.H * g.W * g.C;
+  if (i >= total) return;
+  const int c = (int)(i % g.C);
+  long long r = i / g.C;
+  const int w = (int)(r % g.W); r /= g.W;
+  const int h = (int)(r % g.H); r /= g.H;
+  const int t = (int)(r % g.T);
+  const int n = (int)(r / g.T);
+  float acc = 0.0f;
+  // windows (ot, oh, ow) with ot*ST + kt - PT == t  ->  kt = t + PT - ot*ST in [0, KT)
+  for (int kt = 0; kt < g.KT; ++kt) {
+    const int tn = t + g.PT - kt;
+    if (tn < 0 || tn % g.ST) continue;
+    const int ot = tn / g.ST;
+    if (ot >= g.OT) continue;
+    for (int kh = 0; kh < g.KH; ++kh) {
+      const int hn = h + g.PH - kh;
+      if (hn < 0 || hn % g.SH) continue;
+      const int oh = hn / g.SH;
+      if (oh >= g.OH) continue;
+      for (int kw = 0; kw < g.KW; ++kw) {
+        const int wn = w + g.PW - kw;
+        if (wn < 0 || wn % g.SW) continue;
+        const int ow = wn / g.SW;
+        if (ow >= g.OW) continue;
+        const size_t o = (((size_t)n * g.OT + ot) * g.OH + oh) * g.OW + ow;
+        if (arg[o * g.C + c] == (uint8_t)((kt * g.KH + kh) * g.KW + kw)) acc += __half2float(dy[o * dy_ld + c]);
+      }
+    }
+  }
+  __half* d = dx + ((((size_t)n * g.T + t) * g.H + h) * g.W + w) * dx_ld + c;
+  *d = __float2half_rn(__half2float(*d) + acc);
+}
+
 // ---- 1x1 convolution weight gradient on the tensor cores ------------------------------------------------------------
 // dW[co][ci] = sum_m dz[m][co] * x[m][ci].  A CTA owns a 64 (co) x 64 (ci) tile of dW and one chunk of kWgChunk pixels;
 // both operands are staged [32 pixels][64 channels] in shared memory and fed to wmma (fp16 x fp16 -> fp32) as A^T
@@ -298,13 +451,21 @@ __global__ void __launch_bounds__(256) linear_bwd_dx_kernel(const float* __restr
 // partial tiles are summed by a second kernel in chunk order (deterministic), which also applies `scale`.
 constexpr int kWgTile = 64, kWgPix = 32, kWgChunk = 2048;
 
+// Filters larger than 1x1x1 (stride 1): tap (kt, kh, kw) pairs output pixel (n, t, h, w) with input pixel
+// (t + kt - PT, h + kh - PH, w + kw - PW), zero outside the map (the TF-"SAME" padding, i3dpt.py:14-31); blockIdx.y also
+// enumerates the taps and the staging of x applies the shift.
+struct WgGeom { int T, H, W, KT, KH, KW, PT, PH, PW, taps; };
+
 __global__ void __launch_bounds__(128) conv1x1_wgrad_partial_kernel(const __half* __restrict__ dz, int dz_ld,
                                                                     const __half* __restrict__ x, int x_ld, int M, int Cout,
-                                                                    int Cin, float* __restrict__ partial) {
+                                                                    int Cin, WgGeom wg, float* __restrict__ partial) {
   using namespace nvcuda;
   __shared__ __align__(32) __half sA[kWgPix][kWgTile + 8];
   __shared__ __align__(32) __half sB[kWgPix][kWgTile + 8];
-  const int co0 = blockIdx.x * kWgTile, ci0 = blockIdx.y * kWgTile, chunk = blockIdx.z;
+  const int tiles_ci = gridDim.y / wg.taps;
+  const int tap = blockIdx.y / tiles_ci;
+  const int co0 = blockIdx.x * kWgTile, ci0 = (blockIdx.y - tap * tiles_ci) * kWgTile, chunk = blockIdx.z;
+  const int dkw = tap % wg.KW - wg.PW, dkh = (tap / wg.KW) % wg.KH - wg.PH, dkt = tap / (wg.KW * wg.KH) - wg.PT;
   const int m_beg = chunk * kWgChunk, m_end = min(M, m_beg + kWgChunk);
   const int warp = threadIdx.x >> 5;                 // 4 warps: warp w owns rows (co) [16 w, 16 w + 16) x all 64 ci
   wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[4];
@@ -318,7 +479,15 @@ __global__ void __launch_bounds__(128) conv1x1_wgrad_partial_kernel(const __half
       uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
       if (m < m_end) {
         if (co0 + v * 8 < Cout) a = *reinterpret_cast<const uint4*>(dz + (size_t)m * dz_ld + co0 + v * 8);
-        if (ci0 + v * 8 < Cin) b = *reinterpret_cast<const uint4*>(x + (size_t)m * x_ld + ci0 + v * 8);
+        long long src = m;
+        bool ok = true;
+        if (wg.taps > 1) {
+          const int w = m % wg.W, h = (m / wg.W) % wg.H, t = (m / (wg.W * wg.H)) % wg.T;
+          const int ws = w + dkw, hs = h + dkh, ts = t + dkt;
+          ok = ws >= 0 && ws < wg.W && hs >= 0 && hs < wg.H && ts >= 0 && ts < wg.T;
+          src = (long long)m + ((long long)dkt * wg.H + dkh) * wg.W + dkw;
+        }
+        if (ok && ci0 + v * 8 < Cin) b = *reinterpret_cast<const uint4*>(x + (size_t)src * x_ld + ci0 + v * 8);
       }
       *reinterpret_cast<uint4*>(&sA[r][v * 8]) = a;
       *reinterpret_cast<uint4*>(&sB[r][v * 8]) = b;
@@ -337,23 +506,26 @@ __global__ void __launch_bounds__(128) conv1x1_wgrad_partial_kernel(const __half
     }
     __syncthreads();
   }
-  float* out = partial + ((size_t)chunk * gridDim.x * gridDim.y + (size_t)blockIdx.x * gridDim.y + blockIdx.y) * (kWgTile * kWgTile);
+  float* out = partial + ((size_t)chunk * gridDim.x * gridDim.y + (size_t)blockIdx.x * gridDim.y + blockIdx.y) * (kWgTile * kWgTile);   // [chunk][co tile][tap][ci tile]
 #pragma unroll
   for (int j = 0; j < 4; ++j) wmma::store_matrix_sync(out + (warp * 16) * kWgTile + j * 16, acc[j], kWgTile, wmma::mem_row_major);
 }
 
+// partial tiles are laid out [chunk][co tile][tap][ci tile][64 x 64]; dw is [Cout][taps][dw_ld >= Cin]
 __global__ void __launch_bounds__(256) conv1x1_wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int tiles_co,
-                                                                   int tiles_ci, int Cout, int Cin, float scale,
+                                                                   int tiles_ci, int taps, int Cout, int Cin, float scale,
                                                                    float* __restrict__ dw, int dw_ld, int accumulate) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)Cout * Cin) return;
-  const int co = (int)(i / Cin), ci = (int)(i - (long long)co * Cin);
+  if (i >= (long long)Cout * taps * Cin) return;
+  const int ci = (int)(i % Cin);
+  const int tap = (int)((i / Cin) % taps);
+  const int co = (int)(i / ((long long)Cin * taps));
   const int tco = co / kWgTile, tci = ci / kWgTile;
-  const size_t off = ((size_t)tco * tiles_ci + tci) * (kWgTile * kWgTile) + (size_t)(co - tco * kWgTile) * kWgTile + (ci - tci * kWgTile);
-  const size_t stride = (size_t)tiles_co * tiles_ci * (kWgTile * kWgTile);
+  const size_t off = (((size_t)tco * taps + tap) * tiles_ci + tci) * (kWgTile * kWgTile) + (size_t)(co - tco * kWgTile) * kWgTile + (ci - tci * kWgTile);
+  const size_t stride = (size_t)tiles_co * taps * tiles_ci * (kWgTile * kWgTile);
   float acc = 0.0f;
   for (int c = 0; c < chunks; ++c) acc += partial[off + (size_t)c * stride];   // chunk order: deterministic
-  float* d = dw + (size_t)co * dw_ld + ci;
+  float* d = dw + ((size_t)co * taps + tap) * dw_ld + ci;
   *d = accumulate ? *d + acc * scale : acc * scale;
 }
 
@@ -420,10 +592,11 @@ extern "C" int step_linear_small_n_bwd(const void* x, int dtype, int M, int K, i
   return 0;
 }
 
-extern "C" size_t step_conv1x1_wgrad_workspace_bytes(int M, int Cout, int Cin) {
+extern "C" size_t step_conv_wgrad_workspace_bytes(int M, int Cout, int Cin, int taps) {
   const size_t chunks = (size_t)ceil_div(M, kWgChunk), tco = (size_t)ceil_div(Cout, kWgTile), tci = (size_t)ceil_div(Cin, kWgTile);
-  return chunks * tco * tci * kWgTile * kWgTile * sizeof(float);
+  return chunks * tco * tci * (size_t)(taps > 0 ? taps : 1) * kWgTile * kWgTile * sizeof(float);
 }
+extern "C" size_t step_conv1x1_wgrad_workspace_bytes(int M, int Cout, int Cin) { return step_conv_wgrad_workspace_bytes(M, Cout, Cin, 1); }
 
 extern "C" int step_conv1x1_wgrad_f16(const void* dz, int dz_ld, const void* x, int x_ld, int M, int Cout, int Cin, float scale,
                                       float* dw, int dw_ld, int accumulate, void* workspace, size_t ws_bytes,
@@ -435,11 +608,87 @@ extern "C" int step_conv1x1_wgrad_f16(const void* dz, int dz_ld, const void* x, 
   if (ws_bytes < step_conv1x1_wgrad_workspace_bytes(M, Cout, Cin))
     return fail(STEP_E_WORKSPACE, "conv1x1_wgrad: workspace %zu < %zu", ws_bytes, step_conv1x1_wgrad_workspace_bytes(M, Cout, Cin));
   const int chunks = ceil_div(M, kWgChunk), tco = ceil_div(Cout, kWgTile), tci = ceil_div(Cin, kWgTile);
+  WgGeom wg = {1, 1, M, 1, 1, 1, 0, 0, 0, 1};
   conv1x1_wgrad_partial_kernel<<<dim3(tco, tci, chunks), 128, 0, cu(stream)>>>((const __half*)dz, dz_ld, (const __half*)x, x_ld, M, Cout,
-                                                                               Cin, (float*)workspace);
+                                                                               Cin, wg, (float*)workspace);
   STEP_LAUNCH_CHECK("conv1x1_wgrad_partial_kernel");
-  conv1x1_wgrad_reduce_kernel<<<ceil_div((long long)Cout * Cin, 256), 256, 0, cu(stream)>>>((const float*)workspace, chunks, tco, tci,
+  conv1x1_wgrad_reduce_kernel<<<ceil_div((long long)Cout * Cin, 256), 256, 0, cu(stream)>>>((const float*)workspace, chunks, tco, tci, 1,
                                                                                             Cout, Cin, scale, dw, dw_ld, accumulate);
   STEP_LAUNCH_CHECK("conv1x1_wgrad_reduce_kernel");
+  return 0;
+}
+
+extern "C" int step_conv_wgrad_f16(const void* dz, int dz_ld, const void* x, int x_ld, int N, int T, int H, int W, int Cout, int Cin,
+                                   int KT, int KH, int KW, int PT, int PH, int PW, float scale, float* dw, int dw_ld, int accumulate,
+                                   void* workspace, size_t ws_bytes, step_stream_t stream) {
+  const long long M = (long long)N * T * H * W;
+  const int taps = KT * KH * KW;
+  STEP_CHECK_ARG(M > 0 && M < (1LL << 31) && Cout > 0 && Cin > 0 && taps > 0 && dz && x && dw && workspace, "conv_wgrad: bad arguments");
+  STEP_CHECK_ARG(Cout % 8 == 0 && Cin % 8 == 0 && dz_ld % 8 == 0 && x_ld % 8 == 0 && dz_ld >= Cout && x_ld >= Cin && dw_ld >= Cin,
+                 "conv_wgrad: channel counts / strides must be multiples of 8");
+  STEP_CHECK_ARG((((uintptr_t)dz | (uintptr_t)x) & 15) == 0, "conv_wgrad: pointers must be 16-byte aligned");
+  STEP_CHECK_ARG(PT >= 0 && PT < KT && PH >= 0 && PH < KH && PW >= 0 && PW < KW, "conv_wgrad: bad padding");
+  if (ws_bytes < step_conv_wgrad_workspace_bytes((int)M, Cout, Cin, taps))
+    return fail(STEP_E_WORKSPACE, "conv_wgrad: workspace %zu < %zu", ws_bytes, step_conv_wgrad_workspace_bytes((int)M, Cout, Cin, taps));
+  const int chunks = ceil_div(M, kWgChunk), tco = ceil_div(Cout, kWgTile), tci = ceil_div(Cin, kWgTile);
+  STEP_CHECK_ARG((long long)tci * taps <= 65535 && chunks <= 65535, "conv_wgrad: grid too large");
+  WgGeom wg = {T, H, W, KT, KH, KW, PT, PH, PW, taps};
+  conv1x1_wgrad_partial_kernel<<<dim3(tco, tci * taps, chunks), 128, 0, cu(stream)>>>((const __half*)dz, dz_ld, (const __half*)x, x_ld, (int)M,
+                                                                                      Cout, Cin, wg, (float*)workspace);
+  STEP_LAUNCH_CHECK("conv_wgrad_partial_kernel");
+  conv1x1_wgrad_reduce_kernel<<<ceil_div((long long)Cout * taps * Cin, 256), 256, 0, cu(stream)>>>((const float*)workspace, chunks, tco, tci,
+                                                                                                   taps, Cout, Cin, scale, dw, dw_ld, accumulate);
+  STEP_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
+  return 0;
+}
+
+extern "C" int step_act_bwd_f16(const void* dy, int dy_ld, const void* y, int y_ld, const float* scale, int relu, long long M, int C,
+                                void* dz, int dz_ld, void* dres, int dres_ld, step_stream_t stream) {
+  STEP_CHECK_ARG(M > 0 && C > 0 && C % 8 == 0 && dy_ld % 8 == 0 && dz_ld % 8 == 0 && dy && dz && (!relu || (y && y_ld % 8 == 0)) &&
+                 (!dres || dres_ld % 8 == 0), "act_bwd: bad arguments");
+  STEP_CHECK_ARG((((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dz | (uintptr_t)dres) & 15) == 0, "act_bwd: pointers must be 16-byte aligned");
+  act_bwd_kernel<<<ceil_div(M * (C / 8), 256), 256, 0, cu(stream)>>>((const __half*)dy, dy_ld, (const __half*)y, y_ld, scale, relu, M, C,
+                                                                    (__half*)dz, dz_ld, (__half*)dres, dres_ld);
+  STEP_LAUNCH_CHECK("act_bwd_kernel");
+  return 0;
+}
+
+extern "C" int step_colsum_f16(const void* x, int ld, long long M, int C, float scale, float* out, float* workspace /* >= 64*C floats */,
+                               step_stream_t stream) {
+  STEP_CHECK_ARG(x && out && workspace && M > 0 && C > 0, "colsum: bad arguments");
+  const int chunks = (int)(M < 64 ? M : 64);
+  const int rows_per = ceil_div(M, chunks);
+  colsum_partial_kernel<<<dim3(ceil_div(C, 256), chunks), 256, 0, cu(stream)>>>((const __half*)x, ld, M, C, rows_per, workspace);
+  STEP_LAUNCH_CHECK("colsum_partial_kernel");
+  colsum_reduce_kernel<<<ceil_div(C, 256), 256, 0, cu(stream)>>>(workspace, chunks, C, scale, out);
+  STEP_LAUNCH_CHECK("colsum_reduce_kernel");
+  return 0;
+}
+
+extern "C" int step_mean_mid_bwd(const float* g, int A, int B, int P, int C, float gscale, void* dx, int ld, step_stream_t stream) {
+  STEP_CHECK_ARG(g && dx && A > 0 && B > 0 && P > 0 && C > 0 && ld >= C, "mean_mid_bwd: bad arguments");
+  mean_mid_bwd_kernel<<<ceil_div((long long)A * B * P * C, 256), 256, 0, cu(stream)>>>(g, A, B, P, C, gscale, (__half*)dx, ld);
+  STEP_LAUNCH_CHECK("mean_mid_bwd_kernel");
+  return 0;
+}
+
+extern "C" int step_f32_accum_f16(const float* src, long long M, int C, float gscale, void* dst, int ld, step_stream_t stream) {
+  STEP_CHECK_ARG(src && dst && M > 0 && C > 0 && ld >= C, "f32_accum_f16: bad arguments");
+  f32_accum_f16_kernel<<<ceil_div(M * C, 256), 256, 0, cu(stream)>>>(src, M, C, gscale, (__half*)dst, ld);
+  STEP_LAUNCH_CHECK("f32_accum_f16_kernel");
+  return 0;
+}
+
+extern "C" int step_maxpool3d_bwd_f16(const void* x, int x_ld, const void* dy, int dy_ld, int N, int T, int H, int W, int C, int KT,
+                                      int KH, int KW, int ST, int SH, int SW, int PT, int PH, int PW, int pad_hi_t, int pad_hi_h,
+                                      int pad_hi_w, int OT, int OH, int OW, void* dx /* accumulated in place */, int dx_ld, uint8_t* argmax_ws /* N*OT*OH*OW*C bytes */,
+                                      step_stream_t stream) {
+  STEP_CHECK_ARG(x && dy && dx && argmax_ws && N > 0 && T > 0 && H > 0 && W > 0 && C > 0 && KT * KH * KW < 254, "maxpool3d_bwd: bad arguments");
+  PoolGeom g = {N, T, H, W, C, KT, KH, KW, ST, SH, SW, PT, PH, PW, OT, OH, OW, pad_hi_t, pad_hi_h, pad_hi_w};
+  const long long n_out = (long long)N * OT * OH * OW * C, n_in = (long long)N * T * H * W * C;
+  maxpool_argmax_kernel<<<ceil_div(n_out, 256), 256, 0, cu(stream)>>>(g, (const __half*)x, x_ld, argmax_ws);
+  STEP_LAUNCH_CHECK("maxpool_argmax_kernel");
+  maxpool_bwd_kernel<<<ceil_div(n_in, 256), 256, 0, cu(stream)>>>(g, (const __half*)dy, dy_ld, argmax_ws, (__half*)dx, dx_ld);
+  STEP_LAUNCH_CHECK("maxpool_bwd_kernel");
   return 0;
 }

@@ -20,6 +20,9 @@ A_MODE = {"box": L.A_BOX, "im2col": L.A_IM2COL, "auto": L.A_AUTO, "simt": L.A_SI
 # When set to a list, conv() appends (params, tensors-kept-alive) for every launch: bench.py replays
 # exactly those launches to time the dominant kernel class in isolation (roofline.achieved).
 RECORDER = None
+# When set to a list, conv() and maxpool() append what the backward pass needs (step_b200/training.py): operands, outputs,
+# geometry and the owning parameter container(s) (`tag`).  Activations stay alive through the tape.
+TAPE = None
 DEBUG_SYNC = os.environ.get("STEP_B200_DEBUG_SYNC", "0") == "1"
 STEM_HALO = os.environ.get("STEP_B200_STEM_HALO", "1") != "0"
 
@@ -169,7 +172,7 @@ def params_key(*tensors):
 
 
 def conv(x, w_packed, scale, shift, out, k, stride=(1, 1, 1), pad_lo=None, relu=True, residual=None,
-         a_mode=None, out_dims=None, extra_outs=None, zero_cin_last_kt=0):
+         a_mode=None, out_dims=None, extra_outs=None, zero_cin_last_kt=0, tag=None):
     """Launch step_conv3d_fwd: x (Act) * w_packed [Cout, taps, w_ld] -> out (Act slice).
     extra_outs: up to two more Act slices; output channels are then split [out.C | extra[0].C | extra[1].C]
     (horizontally fused 1x1x1 layers sharing the input)."""
@@ -217,6 +220,9 @@ def conv(x, w_packed, scale, shift, out, k, stride=(1, 1, 1), pad_lo=None, relu=
         except Exception:
             print("conv fault:", {f: getattr(p, f) for f, _ in p._fields_ if isinstance(getattr(p, f), int)}, flush=True)
             raise
+    if TAPE is not None:
+        TAPE.append(dict(kind="conv", x=x, w=w_packed, scale=scale, out=out, extra_outs=list(extra_outs or []), k=tuple(k),
+                         stride=tuple(stride), pad_lo=tuple(pad_lo), relu=bool(relu), residual=residual, tag=tag))
     if RECORDER is not None:
         RECORDER.append((p, (x.buf, w_packed, scale, shift, out.buf, residual.buf if residual is not None else None,
                              [e.buf for e in (extra_outs or [])])))
@@ -240,6 +246,8 @@ def maxpool(x, k, s, out=None):
     L.check(L.lib().step_maxpool3d_fwd(L.c_void_p(x.data_ptr()), x.code, x.N, x.T, x.H, x.W, x.C, x.ld, k[0], k[1],
                                        k[2], s[0], s[1], s[2], pt, ph, pw, ht, hh, hw, ot, oh, ow,
                                        L.c_void_p(out.data_ptr()), out.ld, L.stream()))
+    if TAPE is not None:
+        TAPE.append(dict(kind="pool", x=x, out=out, k=tuple(k), stride=tuple(s), pad_lo=(pt, ph, pw), pad_hi=(ht, hh, hw)))
     return out
 
 

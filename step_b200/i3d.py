@@ -65,7 +65,7 @@ class Unit3Dpy(torch.nn.Module):
         if out is None:
             od = dims or E.same_out_dims((x.T, x.H, x.W), self.kernel_size, self.stride)
             out = Act.empty(x.N, od[0], od[1], od[2], self.conv3d.out_channels, x.code, x.device)
-        return E.conv(x, w, scale, shift, out, self.kernel_size, self.stride, pad_lo, relu, residual, out_dims=dims)
+        return E.conv(x, w, scale, shift, out, self.kernel_size, self.stride, pad_lo, relu, residual, out_dims=dims, tag=self)
 
     def forward_s2d(self, x_s2d):
         """fp16 stem: x_s2d is the space-to-depth clip [N, T/2, H/2, W/2, 32]; 4x4x4 filter, pad 1."""
@@ -152,7 +152,8 @@ class Mixed(torch.nn.Module):
         t2 = Act.empty(x.N, x.T, x.H, x.W, m2, x.code, x.device)
 
         def trunk():
-            E.conv(x, w, scale, shift, out.slice(0, c0), (1, 1, 1), extra_outs=[t1, t2])
+            E.conv(x, w, scale, shift, out.slice(0, c0), (1, 1, 1), extra_outs=[t1, t2],
+                   tag=[self.branch_0, self.branch_1[0], self.branch_2[0]])
 
         def tail():
             E.run_parallel(x.device,

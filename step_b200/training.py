@@ -98,3 +98,179 @@ def conv1x1_wgrad(dz, x, scale=1.0, out=None, accumulate=False):
         L.check(L.lib().step_conv1x1_wgrad_f16(L.ptr(dz), dz.stride(0), L.ptr(x), x.stride(0), M, Cout, Cin, float(scale), L.ptr(dw),
                                                dw.stride(0), 1 if accumulate else 0, L.ptr(ws), nbytes, L.stream()))
     return dw
+
+
+# ---- backward of the tcgen05 / pool tape ------------------------------------------------------------------------------
+class GradStore:
+    """fp16 gradient buffers, one per activation buffer of the forward (same shape, zero-initialised on first use).
+    Every consumer ACCUMULATES into the slice it read, so fan-out (Inception branches, residuals, the shared concat
+    buffer of two_branch.py:256) needs no special casing."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def of(self, act):
+        """Act view of the gradient of `act` (same channel slice of the gradient buffer)."""
+        from .engine import Act
+        key = act.buf.data_ptr()
+        g = self.bufs.get(key)
+        if g is None:
+            g = torch.zeros_like(act.buf)
+            self.bufs[key] = g
+        # `act` may be another view of the same memory (Act.frames(): [N*T, 1, H, W, ld] over [N, T, H, W, ld])
+        return Act(g.view(act.buf.shape), act.C, act.coff)
+
+
+def _dgrad_weights(entry):
+    """[Cout, taps, cin_pad] forward weights -> [Cin, taps, Cout] for the input gradient: dx = conv(dz, flip(w)^T)."""
+    c = entry.get("_wT")
+    if c is None:
+        cin = entry["x"].C
+        c = entry["w"][:, :, :cin].flip(1).permute(2, 1, 0).contiguous()
+        entry["_wT"] = c
+    return c
+
+
+def tape_backward(tape, grads, loss_scale=1.0, need_input_grad=None):
+    """Reverse pass over the conv / max-pool tape recorded by engine.TAPE (fp16 path).  `grads` (GradStore) must already
+    hold d(loss * loss_scale)/d(output) of the last layers.  Returns {parameter tensor: fp32 gradient in the parameter's
+    own layout} (BatchNorm is frozen, i3dpt / networks.py:136-142: only conv weights and biases train).
+    The input gradient of every layer is produced by the SAME tcgen05 convolution kernels run on the transposed, flipped
+    filter (stride-1 convolutions: dx = conv(dz, flip(w)^T)), accumulated through their residual input."""
+    from . import engine as E
+    from .engine import Act
+    out = {}
+    lib = L.lib()
+    inv = 1.0 / float(loss_scale)
+
+    def add(param, g):
+        out[param] = out[param] + g if param in out else g
+
+    for e in reversed(tape):
+        if e["kind"] == "pool":
+            x, y = e["x"], e["out"]
+            gy, gx = grads.of(y), grads.of(x)
+            k, s, pl, ph = e["k"], e["stride"], e["pad_lo"], e["pad_hi"]
+            ws = torch.empty((y.N * y.T * y.H * y.W * y.C,), dtype=torch.uint8, device=x.device)
+            L.check(lib.step_maxpool3d_bwd_f16(L.c_void_p(x.data_ptr()), x.ld, L.c_void_p(gy.data_ptr()), gy.ld, x.N, x.T, x.H, x.W,
+                                               x.C, k[0], k[1], k[2], s[0], s[1], s[2], pl[0], pl[1], pl[2], ph[0], ph[1], ph[2],
+                                               y.T, y.H, y.W, L.c_void_p(gx.data_ptr()), gx.ld, L.ptr(ws), L.stream()))
+            continue
+        x, w, k = e["x"], e["w"], e["k"]
+        if e["stride"] != (1, 1, 1):
+            raise NotImplementedError("tape_backward: strided convolution (the trunk's stem) is not built")
+        outs = [e["out"]] + e["extra_outs"]
+        M = x.N * x.T * x.H * x.W
+        n_total = sum(o.C for o in outs)
+        dz = torch.empty((x.N, x.T, x.H, x.W, n_total), dtype=torch.float16, device=x.device)
+        col = 0
+        for o in outs:
+            gy = grads.of(o)
+            sc = e["scale"][col:col + o.C] if e["scale"] is not None else None
+            res = e["residual"]
+            gres = grads.of(res) if res is not None else None
+            L.check(lib.step_act_bwd_f16(L.c_void_p(gy.data_ptr()), gy.ld, L.c_void_p(o.data_ptr()), o.ld, L.ptr(sc), 1 if e["relu"] else 0,
+                                         M, o.C, L.c_void_p(dz.data_ptr() + 2 * col), n_total,
+                                         L.c_void_p(gres.data_ptr()) if gres is not None else None, gres.ld if gres is not None else 0,
+                                         L.stream()))
+            col += o.C
+        # ---- weight (and bias) gradients
+        taps = k[0] * k[1] * k[2]
+        dw = torch.empty((n_total, taps, x.C), dtype=torch.float32, device=x.device)
+        nbytes = lib.step_conv_wgrad_workspace_bytes(M, n_total, x.C, taps)
+        ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=x.device)
+        pl = e["pad_lo"]
+        L.check(lib.step_conv_wgrad_f16(L.ptr(dz), n_total, L.c_void_p(x.data_ptr()), x.ld, x.N, x.T, x.H, x.W, n_total, x.C, k[0], k[1],
+                                        k[2], pl[0], pl[1], pl[2], inv, L.ptr(dw), x.C, 0, L.ptr(ws), nbytes, L.stream()))
+        tags = e["tag"] if isinstance(e["tag"], (list, tuple)) else [e["tag"]]
+        row = 0
+        for tg, o in zip(tags, outs):
+            if tg is None:
+                row += o.C
+                continue
+            conv = getattr(tg, "conv3d", tg)          # Unit3Dpy holds its nn.Conv3d; nn.Conv2d / nn.Conv3d containers are themselves
+            g = dw[row:row + o.C].view((o.C,) + tuple(conv.weight.shape[2:]) + (x.C,))
+            g = g.permute(0, g.dim() - 1, *range(1, g.dim() - 1)).contiguous()        # [Cout, Cin, *k]
+            if conv.weight.requires_grad:
+                add(conv.weight, g)
+            if conv.bias is not None and conv.bias.requires_grad:
+                db = torch.empty((o.C,), dtype=torch.float32, device=x.device)
+                wsb = torch.empty((64 * o.C,), dtype=torch.float32, device=x.device)
+                L.check(lib.step_colsum_f16(L.c_void_p(dz.data_ptr() + 2 * row), n_total, M, o.C, inv, L.ptr(db), L.ptr(wsb), L.stream()))
+                add(conv.bias, db)
+            row += o.C
+        # ---- input gradient: the forward kernel on the transposed, flipped filter, accumulated into grad(x)
+        if need_input_grad is None or need_input_grad(e):
+            gx = grads.of(x)
+            wT = _dgrad_weights(e)
+            pad = tuple(kk - 1 - p for kk, p in zip(k, pl))
+            saved, E.TAPE = E.TAPE, None
+            try:
+                E.conv(Act(dz), wT, None, None, gx, k, (1, 1, 1), pad, relu=False, residual=gx, out_dims=(x.T, x.H, x.W))
+            finally:
+                E.TAPE = saved
+    return out
+
+
+def head_forward_backward(net, global_feat, tubes, targets, context_feat=None, lambda_reg=5.0, lambda_neighbor=1.0,
+                          loss_scale=1024.0):
+    """One training-time evaluation of a TwoBranchNet on the device (train.py:323-347 for one refinement step): forward
+    with targets, the three losses, and the gradient of  mean(loss_cls) + lambda_reg * loss_loc + lambda_neighbor * loss_nb
+    with respect to every trainable parameter of the head and to the pooled ROI features.  fp16 activations / activation
+    gradients with a static loss scale (apex-style), fp32 weight gradients.  Dropout is the identity (eval mode), like the
+    reference's gradient goldens.
+    Returns dict(prob, loc, first, last, losses=(cls, loc, nb), loss, grads={param: grad}, feat_grad=[N,T',832,7,7] fp32)."""
+    from . import engine as E
+    from .engine import Act
+    from .networks import to_act
+    if context_feat is not None:
+        raise NotImplementedError("head_forward_backward: the context branch's backward is not built")
+    if E.dtype_code(net.fp16) != L.F16:
+        raise RuntimeError("head_forward_backward runs on the fp16 path (cfg.fp16=True)")
+    dev = L.same_device(global_feat, tubes, targets)
+    N, Tl, C, Wd, Hd = global_feat.shape
+    fc, ps = net.fc_dim, net.pool_size
+    D = fc * ps * ps
+    with torch.cuda.device(dev), torch.no_grad():
+        cat = Act.empty(N, Tl, Wd, Hd, C + fc, L.F16, dev)
+        src = to_act(global_feat, L.F16)
+        cat.buf[..., :C].copy_(src.buf[..., src.coff:src.coff + C])
+        tape, keep = [], {}
+        saved_tape, saved_bs = E.TAPE, E.BRANCH_STREAMS
+        E.TAPE, E.BRANCH_STREAMS = tape, False          # one stream: the tape order is the execution order
+        try:
+            prob, loc, first, last, logits = net.forward_act(cat, None, None, want_logits=True, keep=keep)
+        finally:
+            E.TAPE, E.BRANCH_STREAMS = saved_tape, saved_bs
+        lc, ll, ln, g = head_losses(logits, loc, first, last, tubes, targets, net.T, lambda_reg, lambda_neighbor, want_grads=True)
+        grads = GradStore()
+        out = {}
+        hw = net._head_weights()
+        unperm = lambda w: w.view(-1, ps * ps, fc).permute(0, 2, 1).reshape(w.shape[0], -1)   # (p*fc + c) -> (c*49 + p)
+        # ---- classifier: logits = mean_t(gconv) . W^T + b   (two_branch.py:246-249)
+        dxbar, dw, db = linear_backward(keep["xbar"], hw["cls_w"], g["logits"])
+        out[net.global_cls.weight] = unperm(dw).reshape(net.global_cls.weight.shape)
+        out[net.global_cls.bias] = db
+        gcat = grads.of(cat)
+        L.check(L.lib().step_mean_mid_bwd(L.ptr(dxbar), N, Tl, ps * ps, fc, float(loss_scale),
+                                          L.c_void_p(gcat.data_ptr() + 2 * C), gcat.ld, L.stream()))
+        # ---- regressors (two_branch.py:261-270): local_reg on every frame, neighbor_reg1 / 2 on the first / last chunk
+        lf2 = keep["local_feat2"]
+        lf2v = lf2.buf.view(N, Tl, D)
+        s0, s1, e0, e1 = keep["slices"]
+        dlf2 = torch.zeros((N, Tl, D), dtype=torch.float32, device=dev)
+        dx, dw, db = linear_backward(lf2v.reshape(N * Tl, D), hw["local_reg_w32"], g["local_loc"].reshape(N * Tl, 4), dx_out=dlf2.view(N * Tl, D))
+        out[net.local_reg.weight], out[net.local_reg.bias] = unperm(dw), db
+        for mod, nm, (a, b), gk in ((net.neighbor_reg1, "neighbor_reg1", (s0, s1), "first_loc"), (net.neighbor_reg2, "neighbor_reg2", (e0, e1), "last_loc")):
+            xs = lf2v[:, a:b].reshape(-1, D).contiguous()
+            dx, dw, db = linear_backward(xs, hw[nm + "_w32"], g[gk].reshape(-1, 4))
+            dlf2[:, a:b] += dx.view(N, b - a, D)                      # disjoint frame ranges of one buffer (host-side glue)
+            out[mod.weight], out[mod.bias] = unperm(dw), db
+        glf2 = grads.of(lf2)
+        L.check(L.lib().step_f32_accum_f16(L.ptr(dlf2), N * Tl * ps * ps, fc, float(loss_scale), L.c_void_p(glf2.data_ptr()), glf2.ld,
+                                           L.stream()))
+        # ---- every convolution and pool of the head, in reverse
+        out.update(tape_backward(tape, grads, loss_scale))
+        fg = grads.of(cat).buf[..., :C].float().mul_(1.0 / loss_scale).permute(0, 1, 4, 2, 3).contiguous()
+    loss = lc.mean() + lambda_reg * ll.mean() + lambda_neighbor * ln.mean()
+    return dict(prob=prob, loc=loc, first=first, last=last, losses=(lc, ll, ln), loss=loss, grads=out, feat_grad=fg)

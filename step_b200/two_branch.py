@@ -80,7 +80,7 @@ def conv2d(mod, x, relu, residual=None, out=None):
     kh, kw = mod.kernel_size
     if out is None:
         out = Act.empty(x.N, 1, x.H, x.W, mod.out_channels, x.code, x.device)
-    return E.conv(x, w, None, bias, out, (1, kh, kw), (1, 1, 1), (0, kh // 2, kw // 2), relu, residual)
+    return E.conv(x, w, None, bias, out, (1, kh, kw), (1, 1, 1), (0, kh // 2, kw // 2), relu, residual, tag=mod)
 
 
 class Bottleneck(nn.Module):
@@ -274,7 +274,7 @@ class TwoBranchNet(nn.Module):
         # downsample: 1x1x1, bias, no activation (two_branch.py:236) -> channels [832, 832+fc) of cat
         w, bias = _packed(self.downsample, code)
         gconv = cat.slice(832, self.fc_dim)
-        E.conv(g, w, None, bias, gconv, (1, 1, 1), relu=False)
+        E.conv(g, w, None, bias, gconv, (1, 1, 1), relu=False, tag=self.downsample)
         hw = self._head_weights()
         D = self.fc_dim * ps * ps
         # temporal mean then classifier (+ context columns) then sigmoid (two_branch.py:246-249,337)
@@ -299,7 +299,7 @@ class TwoBranchNet(nn.Module):
         lf = self.local_conv(cat.frames())
         w2, b2 = _packed(self.downsample2, code)
         lf2 = Act.empty(R * T, 1, ps, ps, self.fc_dim, code, cat.device)
-        E.conv(lf, w2, None, b2, lf2, (1, 1, 1), relu=False)
+        E.conv(lf, w2, None, b2, lf2, (1, 1, 1), relu=False, tag=self.downsample2)
         # the three regressors share their input: one pass with the twelve weight rows (two_branch.py:261-270)
         Tc = self.T
         chunks = int(T / Tc)
