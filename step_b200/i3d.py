@@ -76,7 +76,7 @@ class Unit3Dpy(torch.nn.Module):
         # rt = 1 half is structurally zero (engine.pack_stem_s2d) -> its MMA steps are skipped by the patch kernel
         return E.conv(x_s2d, w, scale, shift, out, (4, 4, 4), (1, 1, 1), (1, 1, 1), self.activation is not None,
                       a_mode=L.A_HALO if E.STEM_HALO else None, out_dims=(x_s2d.T, x_s2d.H, x_s2d.W),
-                      zero_cin_last_kt=4 * self.conv3d.in_channels)
+                      zero_cin_last_kt=4 * self.conv3d.in_channels, tag=("s2d", self))
 
 
 class MaxPool3dTFPadding(torch.nn.Module):

@@ -182,6 +182,15 @@ def tape_backward(tape, grads, loss_scale=1.0, need_input_grad=None):
         pl = e["pad_lo"]
         L.check(lib.step_conv_wgrad_f16(L.ptr(dz), n_total, L.c_void_p(x.data_ptr()), x.ld, x.N, x.T, x.H, x.W, n_total, x.C, k[0], k[1],
                                         k[2], pl[0], pl[1], pl[2], inv, L.ptr(dw), x.C, 0, L.ptr(ws), nbytes, L.stream()))
+        if isinstance(e["tag"], tuple) and e["tag"][0] == "s2d":
+            # the stride-2 7x7x7 stem runs as a 4x4x4 filter over the space-to-depth clip (engine.pack_stem_s2d):
+            # tap q and sub-position r hold filter position k = 2 q + r (k = 7 is padding) -- undo that packing
+            unit = e["tag"][1]
+            cin = unit.conv3d.in_channels
+            g8 = dw[:, :, :8 * cin].reshape(n_total, 4, 4, 4, 2, 2, 2, cin).permute(0, 7, 1, 4, 2, 5, 3, 6).reshape(n_total, cin, 8, 8, 8)
+            if unit.conv3d.weight.requires_grad:
+                add(unit.conv3d.weight, g8[:, :, :7, :7, :7].contiguous())
+            continue                                   # the clip itself needs no gradient
         tags = e["tag"] if isinstance(e["tag"], (list, tuple)) else [e["tag"]]
         row = 0
         for tg, o in zip(tags, outs):
@@ -274,3 +283,59 @@ def head_forward_backward(net, global_feat, tubes, targets, context_feat=None, l
         fg = grads.of(cat).buf[..., :C].float().mul_(1.0 / loss_scale).permute(0, 1, 4, 2, 3).contiguous()
     loss = lc.mean() + lambda_reg * ll.mean() + lambda_neighbor * ln.mean()
     return dict(prob=prob, loc=loc, first=first, last=last, losses=(lc, ll, ln), loss=loss, grads=out, feat_grad=fg)
+
+
+def trunk_forward_backward(base_net, clips, d_feat_fn, loss_scale=1024.0):
+    """I3D trunk forward on the fp16 path with the tape on, then backward from d(loss)/d(conv_feat).
+    d_feat_fn(feat_act) -> fp32 tensor [N,T',H',W',832] (channels-last) with the gradient of the loss w.r.t. the trunk
+    output (e.g. the sum of the ROIAlign backward results of the refinement steps).
+    Returns (feat Act, {conv weight: fp32 gradient}).  BatchNorm stays frozen (networks.py:85-99,136-142)."""
+    from . import engine as E
+    dev = clips.device
+    with torch.cuda.device(dev), torch.no_grad():
+        tape = []
+        saved_tape, saved_bs = E.TAPE, E.BRANCH_STREAMS
+        E.TAPE, E.BRANCH_STREAMS = tape, False
+        try:
+            feat = base_net.forward_act(clips)
+        finally:
+            E.TAPE, E.BRANCH_STREAMS = saved_tape, saved_bs
+        grads = GradStore()
+        gfeat = grads.of(feat)
+        d = d_feat_fn(feat).to(torch.float32).contiguous()
+        M = feat.N * feat.T * feat.H * feat.W
+        L.check(L.lib().step_f32_accum_f16(L.ptr(d), M, feat.C, float(loss_scale), L.c_void_p(gfeat.data_ptr()), gfeat.ld, L.stream()))
+        out = tape_backward(tape, grads, loss_scale)
+    return feat, out
+
+
+def sgd_step(params_and_grads, lr, momentum=0.9, weight_decay=0.0, state=None, world_size=1):
+    """optim.SGD(momentum, weight_decay) (train.py:124) on the fp32 master parameters, after an optional gradient
+    all-reduce over the clip-parallel ranks (NCCL; one flat bucket).  state: dict param -> momentum buffer.
+    Host-side glue over torch.distributed + elementwise updates; the parameters change in place (their packed fp16
+    copies are rebuilt by the modules' version-keyed caches on the next forward)."""
+    state = {} if state is None else state
+    items = [(p, g) for p, g in params_and_grads.items() if p.requires_grad]
+    if world_size > 1 and items:
+        import torch.distributed as dist
+        flat = torch.cat([g.reshape(-1) for _, g in items])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world_size)
+        off = 0
+        for _, g in items:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+    with torch.no_grad():
+        for p, g in items:
+            g = g.to(p.device, p.dtype)
+            if weight_decay:
+                g = g.add(p, alpha=weight_decay)
+            if momentum:
+                buf = state.get(p)
+                if buf is None:
+                    buf = state[p] = g.clone()          # torch.optim.SGD: first step initialises the buffer with the gradient
+                else:
+                    buf.mul_(momentum).add_(g)
+                g = buf
+            p.add_(g, alpha=-lr)
+    return state
