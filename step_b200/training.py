@@ -222,7 +222,7 @@ def tape_backward(tape, grads, loss_scale=1.0, need_input_grad=None):
 
 
 def head_forward_backward(net, global_feat, tubes, targets, context_feat=None, lambda_reg=5.0, lambda_neighbor=1.0,
-                          loss_scale=1024.0):
+                          loss_scale=1024.0, cat=None, objective_scale=1.0):
     """One training-time evaluation of a TwoBranchNet on the device (train.py:323-347 for one refinement step): forward
     with targets, the three losses, and the gradient of  mean(loss_cls) + lambda_reg * loss_loc + lambda_neighbor * loss_nb
     with respect to every trainable parameter of the head and to the pooled ROI features.  fp16 activations / activation
@@ -236,14 +236,19 @@ def head_forward_backward(net, global_feat, tubes, targets, context_feat=None, l
         raise NotImplementedError("head_forward_backward: the context branch's backward is not built")
     if E.dtype_code(net.fp16) != L.F16:
         raise RuntimeError("head_forward_backward runs on the fp16 path (cfg.fp16=True)")
-    dev = L.same_device(global_feat, tubes, targets)
-    N, Tl, C, Wd, Hd = global_feat.shape
     fc, ps = net.fc_dim, net.pool_size
     D = fc * ps * ps
+    if cat is None:
+        dev = L.same_device(global_feat, tubes, targets)
+        N, Tl, C, Wd, Hd = global_feat.shape
+    else:   # ROI features already pooled into the [ROI | downsample] concat buffer (ROINet.pool_into)
+        dev = L.same_device(cat.buf, tubes, targets)
+        N, Tl, Wd, Hd, C = cat.N, cat.T, cat.H, cat.W, cat.ld - fc
     with torch.cuda.device(dev), torch.no_grad():
-        cat = Act.empty(N, Tl, Wd, Hd, C + fc, L.F16, dev)
-        src = to_act(global_feat, L.F16)
-        cat.buf[..., :C].copy_(src.buf[..., src.coff:src.coff + C])
+        if cat is None:
+            cat = Act.empty(N, Tl, Wd, Hd, C + fc, L.F16, dev)
+            src = to_act(global_feat, L.F16)
+            cat.buf[..., :C].copy_(src.buf[..., src.coff:src.coff + C])
         tape, keep = [], {}
         saved_tape, saved_bs = E.TAPE, E.BRANCH_STREAMS
         E.TAPE, E.BRANCH_STREAMS = tape, False          # one stream: the tape order is the execution order
@@ -252,6 +257,9 @@ def head_forward_backward(net, global_feat, tubes, targets, context_feat=None, l
         finally:
             E.TAPE, E.BRANCH_STREAMS = saved_tape, saved_bs
         lc, ll, ln, g = head_losses(logits, loc, first, last, tubes, targets, net.T, lambda_reg, lambda_neighbor, want_grads=True)
+        if objective_scale != 1.0:
+            for k_ in g:
+                g[k_].mul_(objective_scale)
         grads = GradStore()
         out = {}
         hw = net._head_weights()
@@ -280,9 +288,11 @@ def head_forward_backward(net, global_feat, tubes, targets, context_feat=None, l
                                            L.stream()))
         # ---- every convolution and pool of the head, in reverse
         out.update(tape_backward(tape, grads, loss_scale))
-        fg = grads.of(cat).buf[..., :C].float().mul_(1.0 / loss_scale).permute(0, 1, 4, 2, 3).contiguous()
+        gcat = grads.of(cat)
+        fg = gcat.buf[..., :C].float().mul_(1.0 / loss_scale).permute(0, 1, 4, 2, 3).contiguous() if global_feat is not None else None
     loss = lc.mean() + lambda_reg * ll.mean() + lambda_neighbor * ln.mean()
-    return dict(prob=prob, loc=loc, first=first, last=last, losses=(lc, ll, ln), loss=loss, grads=out, feat_grad=fg)
+    return dict(prob=prob, loc=loc, first=first, last=last, losses=(lc, ll, ln), loss=loss, grads=out, feat_grad=fg,
+                roi_grad=Act(gcat.buf, C, 0))
 
 
 def trunk_forward_backward(base_net, clips, d_feat_fn, loss_scale=1024.0):
@@ -339,3 +349,62 @@ def sgd_step(params_and_grads, lr, momentum=0.9, weight_decay=0.0, state=None, w
                 g = buf
             p.add_(g, alpha=-lr)
     return state
+
+
+def train_step(cfg, nets, clips, step_tubes, step_targets, lr=None, momentum=0.9, weight_decay=0.0, lambda_reg=5.0,
+               lambda_neighbor=1.0, loss_scale=1024.0, sgd_state=None, world_size=1):
+    """One optimisation step of train.py:286-348 on the device, for already selected training samples
+    (`train_select`, utils/utils.py:135-423, is the host-side sampling of SURVEY.md section 8f rank 4 and is not built):
+        conv_feat = base_net(clips)                                   train.py:263
+        for each refinement step i: ROI-pool the step's flat tubes, run det_net[i-1] with targets,
+            loss_back += loss_cls.mean() + lambda_reg * loss_loc.mean() + lambda_neighbor * loss_nb.mean()   train.py:323-336
+        loss_back.backward(); optimizer.step()                         train.py:345-348
+    step_tubes[i]: [R_i, T', 5] fp32 (frame index first, as flatten_tubes(batch_idx=True) builds them), step_targets[i]:
+    [R_i, 3, 6 + classes].  Spatial mode only (every step pools the whole T' range).  Context branch off.
+    Returns dict(loss, losses=[(cls, loc, nb)], grads={param: fp32 grad}); updates the parameters when lr is given."""
+    from . import engine as E
+    from .engine import Act
+    base, roi_net = nets["base_net"], nets["roi_net"]
+    dev = clips.device
+    n_steps = len(step_tubes)
+    results, roi_grads = [], []
+    all_grads = {}
+
+    def d_feat(feat):
+        # heads first (they need conv_feat), then the sum of their ROIAlign backward results is the trunk's output gradient
+        total = None
+        for i in range(n_steps):
+            head = nets["det_net%d" % i]
+            flat = step_tubes[i].to(dev).float().contiguous()
+            R, Tl = flat.shape[0], flat.shape[1]
+            if Tl != feat.T:
+                raise NotImplementedError("train_step: temporal chunking of the training step is not built (spatial mode)")
+            cat = Act.empty(R, Tl, head.pool_size, head.pool_size, 832 + head.fc_dim, L.F16, dev)
+            roi_net.pool_into(feat, flat, cat.frames().slice(0, 832), Tl, feat.T, 0)
+            r = head_forward_backward(head, None, flat, step_targets[i].to(dev), lambda_reg=lambda_reg, lambda_neighbor=lambda_neighbor,
+                                      loss_scale=loss_scale, cat=cat)
+            results.append(r)
+            all_grads.update(r["grads"])
+            rg = r["roi_grad"]                                     # fp16, scaled by loss_scale, [R, T', 7, 7, ld] slice [0, 832)
+            gin = roi_align_backward_nhwc_strided(rg, flat.view(-1, 5), 1.0 / 16.0, feat.N * feat.T, feat.H, feat.W)
+            total = gin if total is None else total.add_(gin)
+        return total.mul_(1.0 / loss_scale).view(feat.N, feat.T, feat.H, feat.W, feat.C)
+
+    feat, tg = trunk_forward_backward(base, clips, d_feat, loss_scale)
+    all_grads.update(tg)
+    loss = sum(r["loss"] for r in results)
+    if lr is not None:
+        sgd_state = sgd_step(all_grads, lr, momentum, weight_decay, sgd_state, world_size)
+    return dict(loss=loss, losses=[r["losses"] for r in results], grads=all_grads, sgd_state=sgd_state)
+
+
+def roi_align_backward_nhwc_strided(grad_act, rois, spatial_scale, K, H, W, sampling_ratio=0):
+    """ROIAlign backward from a channel slice of a wider fp16 buffer (Act [R, T', ph, pw, ld] slice of C channels)."""
+    ph, pw, C = grad_act.H, grad_act.W, grad_act.C
+    R = grad_act.N * grad_act.T
+    dev = grad_act.device
+    r = rois.detach().float().contiguous()
+    gin = torch.empty((K, H, W, C), dtype=torch.float32, device=dev)
+    L.check(L.lib().step_roi_align_bwd_nhwc(L.c_void_p(grad_act.data_ptr()), grad_act.code, grad_act.ld, L.ptr(r), R, float(spatial_scale),
+                                            ph, pw, K, H, W, C, int(sampling_ratio), L.ptr(gin), C, L.stream()))
+    return gin
