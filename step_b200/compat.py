@@ -1,5 +1,6 @@
-"""Run the reference's own drivers (test.py / demo.py / train.py of NVlabs/STEP) on step_b200
-without editing them.
+"""Run the reference's own inference drivers (test.py / demo.py of NVlabs/STEP) on step_b200
+without editing them.  (train.py additionally needs its `loss.backward(); optimizer.step()` replaced by one call of
+step_b200.training.train_step: the modules here do not build an autograd graph -- INTEGRATION.md.)
 
     import step_b200.compat as compat
     compat.patch("/path/to/STEP")        # before the driver's own imports run

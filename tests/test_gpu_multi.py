@@ -82,3 +82,32 @@ def test_head_on_another_gpu_like_the_reference_driver():
         pooled = torch.randn(3, 4, 832, 7, 7, device="cuda:0")
         prob = nets["det_net0"](pooled)[0]
     assert prob.device == torch.device(nets["det_net0"].device)
+
+
+@needs2
+def test_two_rank_training_step_all_reduce_equals_averaged_single_process():
+    """train_step.sh's data-parallel update: two ranks, each with its own clip, gradients all-reduced over NCCL inside
+    training.sgd_step -- equals one process that computes both clips' gradients, averages them and applies the same SGD."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _shard_worker as w
+    from step_b200 import training
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "params.npz")
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+               "--master-port", "29733", os.path.join(ROOT, "tests", "_shard_worker.py"), "train", out]
+        r = subprocess.run(cmd, env=dict(os.environ, NCCL_DEBUG="WARN"), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        got = dict(np.load(out))
+    dev = torch.device("cuda", 0)
+    cfg, nets = w.train_nets(dev)
+    grads = []
+    for rank in range(2):
+        x, tubes, tg = w.train_inputs(rank)
+        grads.append(training.train_step(cfg, nets, x.to(dev), [tubes.to(dev)], [tg.to(dev)], lr=None)["grads"])
+    mean = {p: (grads[0][p] + grads[1][p]) / 2 for p in grads[0]}
+    before = w.watched(nets)
+    training.sgd_step(mean, lr=0.05, momentum=0.9, weight_decay=1e-4, world_size=1)
+    after = w.watched(nets)
+    for k in w.WATCH:
+        assert np.abs(after[k] - before[k]).max() > 0                      # the step moved the weights
+        assert np.allclose(got[k], after[k], rtol=1e-5, atol=1e-7), k

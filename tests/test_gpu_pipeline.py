@@ -331,3 +331,92 @@ def test_c4_detection_set_fp16_equals_fp32_reference(golden):
             worst_b = max(worst_b, float(np.abs(bx * 224.0 - r[3:7] * 224.0).max()))
     assert worst_s <= 5e-3 and worst_b <= 1.5, (worst_s, worst_b)
     assert rprob.shape == (2 * N, cfg.num_classes)
+
+
+def test_reference_driver_loop_through_compat_patch():
+    """The structure of the reference's test.py:62-218 (a restatement -- the GPU box has no /root/reference) run against the
+    names the reference imports, after `step_b200.compat.patch()`: `from models import ...`,
+    `from external.maskrcnn_benchmark.roi_layers import nms`, `nn.DataParallel(base_net)`, `.cuda()`,
+    `load_state_dict(checkpoint[...])`, `set_device`, `.eval()`, `inference(...)`, then the per-clip x per-class evaluation
+    loop with `valid_tubes` and `nms` on CPU tensors.  Its detections must equal the on-device post-processing."""
+    import sys
+    from collections import OrderedDict
+    import step_b200.compat as compat
+    saved = {k: sys.modules.get(k) for k in ("models", "external", "external.maskrcnn_benchmark", "external.maskrcnn_benchmark.roi_layers")}
+    try:
+        compat.patch()
+        from models import BaseNet, ROINet, TwoBranchNet                         # test.py:21
+        from external.maskrcnn_benchmark.roi_layers import nms                    # test.py:23
+        from step_b200 import inference, postprocess as pp
+        from step_b200.tube_utils import valid_tubes
+        args = synth.make_cfg(fp16=True, T=4, max_iter=2, NUM_CHUNKS={1: 1, 2: 1}, image_size=(112, 112))
+        args.conf_thresh, args.nms_thresh, args.topk, args.evaluate_topk = 0.3, 0.4, 20, 20
+        checkpoint = {"base_net": OrderedDict(("module." + k, v) for k, v in synth.base_net_state_dict().items())}
+        for i in range(args.max_iter):
+            checkpoint["det_net%d" % i] = synth.head_state_dict(100 + i, args)
+        nets = OrderedDict()                                                      # test.py:62-95
+        nets['base_net'] = BaseNet(args)
+        nets['roi_net'] = ROINet(args.pool_mode, args.pool_size)
+        for i in range(args.max_iter):
+            nets['det_net%d' % i] = TwoBranchNet(args)
+        for key in nets:
+            nets[key] = nets[key].cuda()
+        nets['base_net'] = torch.nn.DataParallel(nets['base_net'], device_ids=[0])
+        for i in range(args.max_iter):
+            nets['det_net%d' % i].to('cuda:0')
+            nets['det_net%d' % i].set_device('cuda:0')
+        nets['base_net'].load_state_dict(checkpoint['base_net'])
+        for i in range(args.max_iter):
+            nets['det_net%d' % i].load_state_dict(checkpoint['det_net%d' % i])
+        for _, net in nets.items():
+            net.eval()
+        images = synth.make_clips(2, 16, 112, 112)
+        tubes = synth.make_proposals(2, 5, 4, 112, 112)
+        width = height = 112
+        with torch.no_grad():                                                     # test.py:121-162
+            conv_feat = nets['base_net'](images.cuda())
+            history, _ = inference(args, conv_feat, None, nets, args.max_iter, tubes)
+            per_step = []
+            for i in range(len(history)):
+                pred_prob = history[i]['pred_prob'].cpu()
+                pred_prob = pred_prob[:, int(pred_prob.shape[1] / 2)]
+                pred_tubes = history[i]['pred_loc'].cpu()
+                pred_tubes = pred_tubes[:, int(pred_tubes.shape[1] / 2)]
+                tubes_nums = history[i]['tubes_nums']
+                tubes_count, clips_out = 0, []
+                for b in range(len(tubes_nums)):                                  # test.py:166-210
+                    seq_start = tubes_count
+                    tubes_count = tubes_count + tubes_nums[b]
+                    cur_prob, cur_tubes = pred_prob[seq_start:seq_start + tubes_nums[b]], pred_tubes[seq_start:seq_start + tubes_nums[b]]
+                    scores_list = []
+                    for cl_ind in range(args.num_classes):
+                        scores = cur_prob[:, cl_ind].reshape(-1)
+                        c_mask = scores.gt(args.conf_thresh)
+                        scores = scores[c_mask]
+                        if len(scores) == 0:
+                            continue
+                        boxes = cur_tubes.clone()[c_mask.unsqueeze(1).expand_as(cur_tubes)].view(-1, 4)
+                        boxes = torch.from_numpy(valid_tubes(boxes.view(-1, 1, 4).numpy())).view(-1, 4)
+                        keep = nms(boxes, scores, args.nms_thresh)
+                        assert keep.device.type == "cpu" and keep.dtype == torch.int64
+                        for j in keep.tolist():
+                            scores_list.append((float(scores[j]), cl_ind, (boxes[j] / torch.tensor([width, height, width, height])).tolist()))
+                    scores_list.sort(key=lambda t: t[0])
+                    scores_list = scores_list[::-1][:args.topk]
+                    clips_out.append(scores_list)
+                per_step.append(clips_out)
+            last = history[-1]
+            det = pp.to_lists(pp.detect(last['pred_prob'], last['pred_loc'], last['tubes_nums'], args.conf_thresh, args.nms_thresh,
+                                        width, height, topk=args.topk))
+        for b in range(2):
+            ref = per_step[-1][b]
+            assert len(ref) == len(det[b]) and len(ref) > 0
+            assert [c for _, c, _ in ref] == [c for _, c, _ in det[b]]
+            for (s, c, bx), (dbx, dc, ds) in zip(ref, det[b]):
+                assert abs(s - ds) <= 1e-6 and np.abs(np.asarray(bx) - dbx).max() <= 1e-5
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

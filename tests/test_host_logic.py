@@ -1,5 +1,6 @@
 """CPU: host-side logic of the package -- weight packing, BN folding, the space-to-depth stem
 rewrite, pooling extents, tube list bookkeeping, state-dict key parity."""
+import pytest
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -71,3 +72,40 @@ def test_state_dict_keys_match_reference_counts():
 def test_oracle_same_pad_table():
     assert om.same_pad(7, 2) == (2, 3) and om.same_pad(3, 1) == (1, 1) and om.same_pad(3, 2) == (0, 1)
     assert E.same_pad(7, 2) == (2, 3) and E.same_pad(1, 1) == (0, 0)
+
+
+@pytest.mark.refonly
+def test_compat_patch_substitutes_the_names_the_reference_drivers_import():
+    """Build container only (needs /root/reference): after compat.patch(<reference root>) the reference's own import
+    lines (test.py:19-25) resolve to step_b200, and its utils.utils.inference IS ours -- without editing a reference file."""
+    import os
+    import sys
+    if not os.path.isdir("/root/reference/models"):
+        pytest.skip("reference tree not present")
+    import step_b200
+    import step_b200.compat as compat
+    saved = dict(sys.modules)
+    saved_path = list(sys.path)
+    try:
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k.startswith("external") or k == "utils" or k.startswith("utils.")]:
+            del sys.modules[k]
+        compat.patch("/root/reference")
+        ns = {}
+        exec("from models import BaseNet, ROINet, TwoBranchNet, ContextNet\n"
+             "from external.maskrcnn_benchmark.roi_layers import nms\n"
+             "from utils.utils import inference\n"
+             "from utils.tube_utils import flatten_tubes, valid_tubes", ns)          # the import lines of test.py:19-25
+        assert ns["BaseNet"] is step_b200.BaseNet and ns["TwoBranchNet"] is step_b200.TwoBranchNet
+        assert ns["nms"] is step_b200.roi_layers.nms and ns["inference"] is step_b200.inference
+        assert ns["valid_tubes"].__module__ == "utils.tube_utils"                    # host helpers stay the reference's own
+        cfg = __import__("step_b200.synth", fromlist=["x"]).make_cfg()
+        net = ns["TwoBranchNet"](cfg)
+        net.load_state_dict(__import__("step_b200.synth", fromlist=["x"]).head_state_dict(100, cfg), strict=True)
+        with pytest.raises(RuntimeError):                                            # no CPU fallback on the hot path
+            net(__import__("torch").zeros(1, 8, 832, 7, 7))
+    finally:
+        sys.path[:] = saved_path
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+        sys.modules.update(saved)

@@ -1,5 +1,5 @@
 """Sum the DRAM traffic of the tcgen05 conv launches of ONE step from an ncu CSV
-(`--metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum`) -> profiles/r1_conv_traffic.json."""
+(`--metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum`) -> profiles/r2_conv_traffic.json."""
 import collections, csv, json, re, sys
 path, out = sys.argv[1], sys.argv[2]
 with open(path) as f:
@@ -20,5 +20,7 @@ step = [l for l in launches[a:b] if re.search(r'conv_umma|conv_halo', l[0])]
 res = {"conv_launches": len(step), "dram_read_bytes": int(sum(l[1] for l in step)), "dram_write_bytes": int(sum(l[2] for l in step)),
        "dram_bytes_per_step": int(sum(l[1] + l[2] for l in step)), "kernel_time_us": round(sum(l[3] for l in step) / 1e3, 1),
        "note": "ncu, cold caches per launch (cache control on), clocks uncontrolled; one eager step at B=8"}
+if len(sys.argv) > 3:
+    res["csrc_sha"] = sys.argv[3]     # hash of step_b200/csrc at capture time: bench.py only reports the traffic of the build it runs
 json.dump(res, open(out, 'w'), indent=1)
 print(res)
