@@ -21,12 +21,14 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from step_b200 import synth
-    B, N, C = 2, 3, 6
-    # rank r owns clips [r*B, (r+1)*B): per-rank seed as in bench.py
+    B, cap = 2, 5
+    # rank r owns clips [r*B, (r+1)*B): per-rank seed as in bench.py; what is gathered has the layout of bench.py's
+    # step(): per clip the compact detections [cap, 8] of step_detect_f32 flattened, then the count (stand-in values here:
+    # the kernels need a GPU; tests/test_gpu_multi.py checks the real thing on 2 GPUs)
     clips = synth.make_clips(B, 4, 8, 8, seed=1234 + rank)
-    det = torch.full((B * N, C + 4), float(rank)) + clips.mean()          # stand-in for [prob | box]
-    gather = torch.empty((world, B * N, C + 4))
-    dist.all_gather_into_tensor(gather.view(-1, C + 4), det)
+    det = torch.full((B, cap * 8 + 1), float(rank)) + clips.mean()
+    gather = torch.empty((world, B, cap * 8 + 1))
+    dist.all_gather_into_tensor(gather.view(-1, cap * 8 + 1), det)
     ms = torch.tensor([10.0 + rank])
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     dist.barrier()
@@ -42,7 +44,7 @@ def test_clip_parallel_gather_two_ranks(tmp_path):
     from step_b200 import synth
     for rank in range(2):
         exp = float(rank) + synth.make_clips(2, 4, 8, 8, seed=1234 + rank).mean()
-        assert torch.allclose(r["gather"][rank], torch.full((6, 10), float(exp)))
+        assert torch.allclose(r["gather"][rank], torch.full((2, 41), float(exp)))
     assert float(r["ms"]) == 11.0
 
 
