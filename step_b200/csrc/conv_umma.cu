@@ -880,6 +880,9 @@ static int pick_bk(int Cin) {
   // STEP_B200_BKPOL=1: widest block that the channel count reaches -- the MMA loop skips the zero-filled 16-channel
   // steps of a tap's last block and TMA does not fetch them, so padding inside a block is (nearly) free
   if (const char* e = getenv("STEP_B200_BKPOL")) { if (e[0] == '1') return Cin > 32 ? 64 : (Cin > 16 ? 32 : 16); }
+  // more than 64 channels: 64-wide blocks; the zero-filled 16-channel steps of the last block are skipped and the layer becomes
+  // eligible for CTA pairs (measured round 2: Cin = 96, Mixed_3b 3x3x3 103 -> 90 us, Mixed_4b 27 -> 23 us vs three 32-wide blocks)
+  if (Cin > 64) return 64;
   int best = 64; long best_cost = -1;
   const int cands[3] = {64, 32, 16};
   for (int i = 0; i < 3; ++i) {

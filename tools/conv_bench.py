@@ -37,6 +37,8 @@ LAYERS = {
     "4c_fused":   (8, 8, 14, 14, 512, 296, (1, 1, 1), None, False),
     "5c_fused":   (88, 8, 7, 7, 832, 624, (1, 1, 1), None, False),
     "5b_b3":      (88, 8, 7, 7, 832, 128, (1, 1, 1), None, False),
+    "4b_b1b":     (8, 8, 14, 14, 96, 208, (3, 3, 3), None, False),
+    "4d_b1b":     (8, 8, 14, 14, 128, 256, (3, 3, 3), None, False),
 }
 names = sys.argv[1:] or list(LAYERS)
 torch.manual_seed(0)
