@@ -131,6 +131,29 @@ def _dgrad_weights(entry):
     return c
 
 
+TIMING = None     # set to {} to collect per-phase device times of tape_backward (tools/train_bench.py)
+
+
+class _Phase:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if TIMING is not None:
+            self.e1.record()
+            TIMING.setdefault(self.name, []).append((self.e0, self.e1))
+
+
+def timing_summary():
+    torch.cuda.synchronize()
+    return {k: round(sum(a.elapsed_time(b) for a, b in v), 2) for k, v in (TIMING or {}).items()}
+
+
 def tape_backward(tape, grads, loss_scale=1.0, need_input_grad=None):
     """Reverse pass over the conv / max-pool tape recorded by engine.TAPE (fp16 path).  `grads` (GradStore) must already
     hold d(loss * loss_scale)/d(output) of the last layers.  Returns {parameter tensor: fp32 gradient in the parameter's
@@ -152,7 +175,8 @@ def tape_backward(tape, grads, loss_scale=1.0, need_input_grad=None):
             gy, gx = grads.of(y), grads.of(x)
             k, s, pl, ph = e["k"], e["stride"], e["pad_lo"], e["pad_hi"]
             ws = torch.empty((y.N * y.T * y.H * y.W * y.C,), dtype=torch.uint8, device=x.device)
-            L.check(lib.step_maxpool3d_bwd_f16(L.c_void_p(x.data_ptr()), x.ld, L.c_void_p(gy.data_ptr()), gy.ld, x.N, x.T, x.H, x.W,
+            with _Phase("pool_bwd"):
+              L.check(lib.step_maxpool3d_bwd_f16(L.c_void_p(x.data_ptr()), x.ld, L.c_void_p(gy.data_ptr()), gy.ld, x.N, x.T, x.H, x.W,
                                                x.C, k[0], k[1], k[2], s[0], s[1], s[2], pl[0], pl[1], pl[2], ph[0], ph[1], ph[2],
                                                y.T, y.H, y.W, L.c_void_p(gx.data_ptr()), gx.ld, L.ptr(ws), L.stream()))
             continue
@@ -164,6 +188,7 @@ def tape_backward(tape, grads, loss_scale=1.0, need_input_grad=None):
         n_total = sum(o.C for o in outs)
         dz = torch.empty((x.N, x.T, x.H, x.W, n_total), dtype=torch.float16, device=x.device)
         col = 0
+        ph_act = _Phase("act_bwd"); ph_act.__enter__()
         for o in outs:
             gy = grads.of(o)
             sc = e["scale"][col:col + o.C] if e["scale"] is not None else None
@@ -174,13 +199,15 @@ def tape_backward(tape, grads, loss_scale=1.0, need_input_grad=None):
                                          L.c_void_p(gres.data_ptr()) if gres is not None else None, gres.ld if gres is not None else 0,
                                          L.stream()))
             col += o.C
+        ph_act.__exit__()
         # ---- weight (and bias) gradients
         taps = k[0] * k[1] * k[2]
         dw = torch.empty((n_total, taps, x.C), dtype=torch.float32, device=x.device)
         nbytes = lib.step_conv_wgrad_workspace_bytes(M, n_total, x.C, taps)
         ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=x.device)
         pl = e["pad_lo"]
-        L.check(lib.step_conv_wgrad_f16(L.ptr(dz), n_total, L.c_void_p(x.data_ptr()), x.ld, x.N, x.T, x.H, x.W, n_total, x.C, k[0], k[1],
+        with _Phase("wgrad_k%d" % taps):
+          L.check(lib.step_conv_wgrad_f16(L.ptr(dz), n_total, L.c_void_p(x.data_ptr()), x.ld, x.N, x.T, x.H, x.W, n_total, x.C, k[0], k[1],
                                         k[2], pl[0], pl[1], pl[2], inv, L.ptr(dw), x.C, 0, L.ptr(ws), nbytes, L.stream()))
         if isinstance(e["tag"], tuple) and e["tag"][0] == "s2d":
             # the stride-2 7x7x7 stem runs as a 4x4x4 filter over the space-to-depth clip (engine.pack_stem_s2d):
@@ -215,7 +242,8 @@ def tape_backward(tape, grads, loss_scale=1.0, need_input_grad=None):
             pad = tuple(kk - 1 - p for kk, p in zip(k, pl))
             saved, E.TAPE = E.TAPE, None
             try:
-                E.conv(Act(dz), wT, None, None, gx, k, (1, 1, 1), pad, relu=False, residual=gx, out_dims=(x.T, x.H, x.W))
+                with _Phase("dgrad"):
+                    E.conv(Act(dz), wT, None, None, gx, k, (1, 1, 1), pad, relu=False, residual=gx, out_dims=(x.T, x.H, x.W))
             finally:
                 E.TAPE = saved
     return out

@@ -30,6 +30,7 @@ tg = tg.cuda()
 # timing of the full step incl. an SGD update.  The update is layer-wise normalised (every tensor moves by 3e-4 of its own norm):
 # the synthetic nets pair regressor weights of std 5e-5 with convolution weights of O(0.05), one global rate cannot suit both
 for it in range(4):
+    training.TIMING = {} if it == 3 else None
     torch.cuda.synchronize(); t0 = time.perf_counter()
     r = training.train_step(cfg, nets, x, [tubes] * 3, [tg] * 3, lr=None)
     for p, g in r["grads"].items():
@@ -39,3 +40,4 @@ for it in range(4):
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(json.dumps({"iter": it, "B": B, "train_step_ms": round(dt * 1e3, 1), "loss": round(float(r["loss"]), 5),
                       "clips_per_s": round(B / dt, 1), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2)}), flush=True)
+print(json.dumps({"device_ms_by_phase_of_the_backward_tape": training.timing_summary()}))
