@@ -269,7 +269,10 @@ def run_ours(args):
         def replay():
             s = _lib.stream()
             for q, _ in rec:
-                _lib.check(real_lib.step_conv3d_fwd(q, s))
+                if isinstance(q, tuple):      # fused bottleneck exit (engine.bottleneck_exit)
+                    _lib.check(real_lib.step_bottleneck_exit_f16(*q[1], s))
+                else:
+                    _lib.check(real_lib.step_conv3d_fwd(q, s))
         replay()
         # the recorded launches back to back on one stream; as a CUDA graph, so that the Python / ctypes launch path
         # (5-10 us per call, longer than the shortest kernels) does not show up as gaps between them
@@ -295,6 +298,9 @@ def run_ours(args):
         # algorithmic bytes of the same launches: input + weights + output (+ residual), fp16
         alg_bytes = 0
         for q, _ in rec:
+            if isinstance(q, tuple):
+                alg_bytes += q[2]
+                continue
             taps = q.KT * q.KH * q.KW
             alg_bytes += 2 * (q.N * q.T * q.H * q.W * q.Cin + q.Cout * taps * q.Cin +
                               q.N * q.OT * q.OH * q.OW * q.Cout * (2 if q.residual else 1))
@@ -312,7 +318,7 @@ def run_ours(args):
                 traffic = None
         flops = ALG_GFLOP_PER_CLIP * 1e9 * B
         achieved = flops / (ms_conv / max(3, args.steps) * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "tcgen05 conv class: conv_umma_kernel + conv_umma_persist_kernel + conv_halo_kernel",
+        roof = {"bound": "tensor", "kernel": "tcgen05 conv class: conv_umma_kernel + conv_umma_persist_kernel + conv_halo_kernel + bottleneck_exit_kernel",
                 "achieved": round(achieved, 2),
                 "peak": pk["tflops"], "peak_source": pk["src"] + " bf16 sustained", "unit": "TFLOP/s",
                 "frac": round(achieved / pk["tflops"], 4), "traffic": traffic, "traffic_unit": "DRAM bytes per step, all conv launches (ncu)", "traffic_source": traffic_src,

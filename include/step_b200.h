@@ -217,6 +217,18 @@ int step_head_regress(const void* x, int dtype, int R, int T, int K, int x_ld, c
                       int s0, int s1, int e0, int e1, float* local_loc, float* first, float* last, void* workspace,
                       size_t ws_bytes, step_stream_t stream);
 
+/* Exit of a 2-D bottleneck of the local branch fused with the 1x1 convolution that consumes it, fp16, channels-last rows:
+ *   y[M, inplanes] = relu(h[M, planes] * w3[inplanes, planes]^T + x[M, inplanes])      Bottleneck.forward, models/two_branch.py:79-83
+ *                                                                                 (Bottleneck_resample.forward, :106-110)
+ *   z[M, outplanes] = act(y * w1[outplanes, inplanes]^T + shift2)                   the next block's conv1 + ReLU (:68-69, relu2 = 1,
+ *                                                                                 shift2 = NULL) or downsample2 (:259, relu2 = 0, bias)
+ * in one launch; y may be NULL when nothing else reads it.  Bit-identical to step_conv3d_fwd called twice.  Built for the
+ * reference's fixed head widths planes = 256, inplanes = 1024, outplanes = 256 (two_branch.py:190-192); other widths return
+ * STEP_E_ARG and the caller launches the two convolutions.  Row pitches in elements. */
+int step_bottleneck_exit_f16(const void* h, long long h_ld, const void* w3, const void* x, long long x_ld, const void* w1,
+                             const float* shift2, int relu2, void* y, long long y_ld, void* z, long long z_ld, long long M,
+                             int planes, int inplanes, int outplanes, step_stream_t stream);
+
 /* ------------------------------------------------------------------ training (first pieces) ---- */
 /* TwoBranchNet's losses (models/two_branch.py:276-333) and, when the d* pointers are given, the gradient of the training
  * objective mean(loss_cls) + w_loc * loss_loc + w_nb * loss_nb (train.py:323-347) with respect to the head outputs.

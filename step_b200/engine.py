@@ -116,6 +116,30 @@ class Act:
         return Act(self.buf.view(self.N * self.T, 1, self.H, self.W, self.ld), self.C, self.coff)
 
 
+FUSE_EXIT = os.environ.get("STEP_B200_FUSE_EXIT", "1") != "0"
+
+
+def bottleneck_exit(h, w3, x, w1, shift2, relu2, z, y=None):
+    """step_bottleneck_exit_f16: y = relu(h * w3^T + x); z = act(y * w1^T + shift2) on frames Acts (rows = N*T*H*W).
+    h [.., planes], x / y [.., inplanes], z [.., outplanes]; w3 / w1 packed 1x1 filters [Cout, 1, Cin] fp16."""
+    L.same_device(h.buf, x.buf, z.buf, w3, w1)
+    M = h.N * h.T * h.H * h.W
+    args = (h.data_ptr(), h.ld, L.ptr(w3), x.data_ptr(), x.ld, L.ptr(w1), L.ptr(shift2) if shift2 is not None else None,
+            1 if relu2 else 0, y.data_ptr() if y is not None else None, y.ld if y is not None else 0, z.data_ptr(), z.ld,
+            M, h.C, x.C, z.C)
+    L.check(L.lib().step_bottleneck_exit_f16(*args, L.stream()))
+    if RECORDER is not None:   # (launch arguments, buffers kept alive, algorithmic bytes) for bench.py's replay of the conv class
+        alg = 2 * (M * (h.C + x.C + z.C + (x.C if y is not None else 0)) + w3.numel() + w1.numel())
+        RECORDER.append((("exit", args, alg), (h.buf, w3, x.buf, w1, shift2, y.buf if y is not None else None, z.buf)))
+    return z
+
+
+def can_fuse_exit(code, planes, inplanes, outplanes):
+    """The fused kernel exists for the reference's head widths and the fp16 path; it does not record the per-layer tape
+    entries the reverse pass walks, so the training forward keeps the two launches."""
+    return FUSE_EXIT and TAPE is None and code == L.F16 and planes == 256 and inplanes == 1024 and outplanes == 256
+
+
 def same_pad(k, s):
     """models/i3dpt.py:14-31 per dimension: (low, high)."""
     pad = max(k - s, 0)

@@ -296,10 +296,7 @@ class TwoBranchNet(nn.Module):
             z = torch.tensor([0.], device=prob.device)
             return (prob, z, z, z, raw) if want_logits else (prob, z, z, z)
         # local branch on frames (two_branch.py:253-262)
-        lf = self.local_conv(cat.frames())
-        w2, b2 = _packed(self.downsample2, code)
-        lf2 = Act.empty(R * T, 1, ps, ps, self.fc_dim, code, cat.device)
-        E.conv(lf, w2, None, b2, lf2, (1, 1, 1), relu=False, tag=self.downsample2)
+        lf, lf2 = self._local_branch(cat.frames(), want_lf=keep is not None)
         # the three regressors share their input: one pass with the twelve weight rows (two_branch.py:261-270)
         Tc = self.T
         chunks = int(T / Tc)
@@ -318,6 +315,44 @@ class TwoBranchNet(nn.Module):
         if keep is not None:   # activations the training pieces need (step_b200/training.py): channels-last layouts
             keep.update(xbar=xbar, local_feat=lf, local_feat2=lf2, slices=(s0, s1, e0, e1))
         return (prob, local_loc, first, last, raw) if want_logits else (prob, local_loc, first, last)
+
+    def _local_branch(self, frames, want_lf=False):
+        """local_conv (Bottleneck_resample + 2 Bottlenecks) and downsample2 on frames (two_branch.py:258-259).  Returns
+        (local_feat or None, local_feat2).  On the fp16 inference path the exit of every block (1x1 conv + residual + ReLU)
+        runs in one launch with the 1x1 convolution that consumes it (engine.bottleneck_exit); otherwise layer by layer."""
+        code = frames.code
+        F, ps = frames.N, self.pool_size
+        blocks = list(self.local_conv)
+        w2, b2 = _packed(self.downsample2, code)
+        lf2 = Act.empty(F, 1, ps, ps, self.fc_dim, code, frames.device)
+        rs = blocks[0]
+        fuse = (len(blocks) == 3 and isinstance(rs, Bottleneck_resample) and all(isinstance(b, Bottleneck) for b in blocks[1:])
+                and E.can_fuse_exit(code, rs.conv4.in_channels, rs.conv4.out_channels, self.fc_dim)
+                and all(b.conv1.in_channels == 1024 and b.conv1.out_channels == 256 and b.conv3.in_channels == 256
+                        and b.conv3.out_channels == 1024 for b in blocks[1:]))
+        if not fuse:
+            lf = self.local_conv(frames)
+            E.conv(lf, w2, None, b2, lf2, (1, 1, 1), relu=False, tag=self.downsample2)
+            return lf, lf2
+        # block 0: conv2 -> conv3 chain beside the residual projection conv1 (two_branch.py:100-110)
+        box = {}
+        E.run_parallel(frames.device,
+                       lambda: box.__setitem__("o", conv2d(rs.conv3, conv2d(rs.conv2, frames, True), True)),
+                       [lambda: box.__setitem__("res", conv2d(rs.conv1, frames, False))])
+        h, x = box["o"], box["res"]
+        w3 = _packed(rs.conv4, code)[0]
+        for nxt in blocks[1:]:
+            # y = relu(conv_exit(h) + x) is the block's output and the next block's residual; z = relu(next.conv1(y))
+            y = Act.empty(F, 1, ps, ps, 1024, code, frames.device)
+            z = Act.empty(F, 1, ps, ps, 256, code, frames.device)
+            E.bottleneck_exit(h, w3, x, _packed(nxt.conv1, code)[0], None, True, z, y)
+            h = conv2d(nxt.conv2, z, True)
+            x = y
+            w3 = _packed(nxt.conv3, code)[0]
+        # last block's exit + downsample2 (bias, no activation); its output is only materialised when a caller keeps it
+        lf = Act.empty(F, 1, ps, ps, 1024, code, frames.device) if want_lf else None
+        E.bottleneck_exit(h, w3, x, w2, b2, False, lf2, lf)
+        return lf, lf2
 
     def _reg12(self, code):
         """[W_local | W_nb1 | W_nb2] (12 x D, permuted to channels-last) in the compute dtype + fp32 biases."""

@@ -370,3 +370,58 @@ def test_halo_kernel_matches_im2col_kernel(case):
     # same products, same fp32 accumulator, different summation order inside the tensor core at most
     err = float((outs[0].float() - outs[1].float()).abs().max())
     assert err <= 2e-3 * float(outs[1].float().abs().max()) + 1e-3, err
+
+
+# ---- fused bottleneck exit (step_bottleneck_exit_f16) -------------------------------------------------------------------
+def _exit_inputs(M, seed, x_pad=0):
+    g = torch.Generator().manual_seed(seed)
+    h = torch.randn(M, 256, generator=g).half().cuda()
+    w3 = (torch.randn(1024, 256, generator=g) / 16).half().cuda()
+    xbuf = torch.randn(M, 1024 + x_pad, generator=g).half().cuda()
+    w1 = (torch.randn(256, 1024, generator=g) / 32).half().cuda()
+    b = torch.randn(256, generator=g).float().cuda()
+    return h, w3, xbuf, w1, b
+
+
+def _frames(t2d, C, coff=0):
+    return Act(t2d.view(t2d.shape[0], 1, 1, 1, t2d.shape[1]), C, coff)
+
+
+@pytest.mark.parametrize("M", [1, 200, 256, 1000, 7 * 7 * 88 * 8])
+@pytest.mark.parametrize("variant", ["next_conv1", "downsample2"])
+def test_bottleneck_exit_equals_two_launches(M, variant):
+    """y = relu(h w3^T + x), z = act(y w1^T + b): one launch == the two step_conv3d_fwd launches it replaces, bit for bit
+    (same fp16 rounding of y, same K order), and both within fp16 accumulation noise of an fp32 evaluation."""
+    x_pad = 64 if M == 1000 else 0                       # residual read out of a wider buffer (row pitch > channels)
+    h, w3, xbuf, w1, b = _exit_inputs(M, 7 + M, x_pad)
+    relu2, bias = (True, None) if variant == "next_conv1" else (False, b)
+    ha, xa = _frames(h, 256), _frames(xbuf, 1024)
+    w3p, w1p = w3.view(1024, 1, 256), w1.view(256, 1, 1024)
+    # two launches
+    y_ref = _frames(torch.empty(M, 1024, dtype=torch.float16, device="cuda"), 1024)
+    z_ref = _frames(torch.empty(M, 256, dtype=torch.float16, device="cuda"), 256)
+    E.conv(ha, w3p, None, None, y_ref, (1, 1, 1), relu=True, residual=xa)
+    E.conv(y_ref, w1p, None, bias, z_ref, (1, 1, 1), relu=relu2)
+    # one launch
+    store_y = variant == "next_conv1"
+    y = _frames(torch.zeros(M, 1024, dtype=torch.float16, device="cuda"), 1024) if store_y else None
+    z = _frames(torch.zeros(M, 256, dtype=torch.float16, device="cuda"), 256)
+    E.bottleneck_exit(ha, w3p, xa, w1p, bias, relu2, z, y)
+    torch.cuda.synchronize()
+    if store_y:
+        assert torch.equal(y.buf, y_ref.buf)
+    assert torch.equal(z.buf, z_ref.buf)
+    yf = torch.relu(h.float() @ w3.float().t() + xbuf[:, :1024].float())
+    zf = yf.half().float() @ w1.float().t()
+    zf = torch.relu(zf) if relu2 else zf + b
+    assert (z.buf.view(M, 256).float() - zf).abs().max().item() <= 2e-3 * zf.abs().max().item() + 1e-3
+
+
+def test_bottleneck_exit_rejects_other_widths():
+    h = _frames(torch.zeros(64, 128, dtype=torch.float16, device="cuda"), 128)
+    x = _frames(torch.zeros(64, 1024, dtype=torch.float16, device="cuda"), 1024)
+    z = _frames(torch.zeros(64, 256, dtype=torch.float16, device="cuda"), 256)
+    w3 = torch.zeros(1024, 1, 128, dtype=torch.float16, device="cuda")
+    w1 = torch.zeros(256, 1, 1024, dtype=torch.float16, device="cuda")
+    with pytest.raises(RuntimeError, match="planes 256"):
+        E.bottleneck_exit(h, w3, x, w1, None, True, z)

@@ -420,3 +420,23 @@ def test_reference_driver_loop_through_compat_patch():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_fused_bottleneck_exit_does_not_change_the_pipeline(golden):
+    """fp16 inference with the fused block exits (step_bottleneck_exit_f16, three launches per refinement step) produces
+    the same bits as the layer-by-layer launches."""
+    from step_b200 import engine as E
+    name = "pipe_spatial"
+    g = golden(name)
+    outs = []
+    old = E.FUSE_EXIT
+    try:
+        for fuse in (True, False):
+            E.FUSE_EXIT = fuse
+            cfg, cf, ctx, hist, traj = run(name, g, True, **PIPES[name])
+            outs.append(hist)
+    finally:
+        E.FUSE_EXIT = old
+    for a, b in zip(*outs):
+        assert torch.equal(a["pred_prob"], b["pred_prob"])
+        assert torch.equal(a["pred_loc"], b["pred_loc"])

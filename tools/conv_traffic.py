@@ -16,7 +16,7 @@ for k, v in per.items():
     launches.append((v['name'], rd[0] * scale.get(rd[1], 1), wr[0] * scale.get(wr[1], 1), t[0] * scale.get(t[1], 1)))
 starts = [i for i, l in enumerate(launches) if 'clip_to_s2d' in l[0]]
 a = starts[0] if starts else 0; b = starts[1] if len(starts) > 1 else len(launches)
-step = [l for l in launches[a:b] if re.search(r'conv_umma|conv_halo', l[0])]
+step = [l for l in launches[a:b] if re.search(r'conv_umma|conv_halo|bottleneck_exit', l[0])]
 res = {"conv_launches": len(step), "dram_read_bytes": int(sum(l[1] for l in step)), "dram_write_bytes": int(sum(l[2] for l in step)),
        "dram_bytes_per_step": int(sum(l[1] + l[2] for l in step)), "kernel_time_us": round(sum(l[3] for l in step) / 1e3, 1),
        "note": "ncu, cold caches per launch (cache control on), clocks uncontrolled; one eager step at B=8"}
