@@ -4,14 +4,25 @@
 //     Y[M, 1024] = relu(H[M, 256] * W3[1024, 256]^T + X[M, 1024])          conv3 + residual + ReLU     (stored unless y == NULL)
 //     Z[M,  256] = act(Y[M, 1024] * W1[256, 1024]^T + shift2)               next conv1 (ReLU) / downsample2 (bias, no ReLU)
 //
-// Today these are two launches, 53 + 24 us: the first is bound by reading its 1024-wide fp32 accumulator out of TMEM and by
+// Today these are two launches, 53 + 20 us: the first is bound by reading its 1024-wide fp32 accumulator out of TMEM and by
 // writing / re-reading the 70 MB activation.  Here a CTA PAIR (cta_group::2, 256 rows) walks the 1024 columns of Y in 16 chunks
-// of 64: GEMM1 chunk -> TMEM (64 columns, double buffered) -> epilogue warps add the residual, ReLU, convert, and write the chunk
-// as a K-major 128B-swizzled A operand into shared memory (the same bytes are bulk-stored to Y) -> GEMM2 accumulates
-// Z += Y_chunk * W1[:, chunk]^T in a second TMEM region (256 columns).  Y never has to be re-read.
+// of 64: the residual chunk is TMA-loaded into a shared-memory buffer in the K-major 128B-swizzled operand layout; GEMM1 chunk
+// -> TMEM (64 columns, 4 buffers) -> epilogue warps add the accumulator to the residual IN PLACE, ReLU, round to fp16 (the
+// buffer is now the A operand of GEMM2 and is also bulk-stored to Y) -> GEMM2 accumulates Z += Y_chunk * W1[:, chunk]^T in a
+// second TMEM region (256 columns).  Y never has to be re-read.
 //
-// Per CTA: warp 0 producer (TMA), warp 1 MMA issuer (leader CTA only), warps 2..5 / 6..9 epilogue groups 0 / 1 (group g owns the
-// chunks with c & 1 == g: accumulator buffer g, A2 buffer g, residual buffer g); all 8 epilogue warps share the final Z epilogue.
+// Per CTA (17 warps): warp 0 loads H and the W3 chunks, warp 1 issues GEMM1 (leader CTA), warps 2-13 are three epilogue groups
+// (chunk c -> group c % 3), warp 14 loads the W1 slices, warp 15 issues GEMM2, warp 16 loads the residual chunks.
+// History of the variants measured on the way (M = 34496, Y stored; the two library launches take 75-78 us):
+//   84 us  one producer thread for W3 + W1, one MMA thread, residual through a shared-memory ring, cluster-scope arrives
+//   75 us  W1 ring on its own producer thread (the shared thread serialised the two rings)
+//   57 us  remote arrives with CTA scope (`mbarrier.arrive.release.cluster` = MEMBAR.ALL.GPU, 2-4k cycles with loads in flight)
+//   52 us  MMA issue without the per-instruction R2UR / ELECT loops of a divergent `lane == 0` branch (`if (elect_one())`)
+//   50 us  residual through registers with a staggered L2 prefetch; GEMM1 and GEMM2 issued by separate warps
+//   62 us  16 half-chunk epilogue warps storing Y with st.global (slower: 64-byte row pieces instead of full-line bulk stores)
+//   47 us  THIS FILE: residual TMA-loaded into the A2 buffer, updated in place; 3 epilogue groups (96 registers / thread)
+// What bounds it now: ~1.15 MB per CTA tile moves between L2 and the SM (W3 + W1 halves 512 KB, X 256 KB, Y 256 KB, H + Z
+// 128 KB) = 310 MB per launch, and every TMA load waits 2-3 us in the SM's queue under that load.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -21,7 +32,9 @@
 
 namespace fexit {
 
-constexpr int kThreads = 384;                   // warp 0: H + W3 loads, 1: GEMM1 issue, 2-9: epilogue, 10: W1 loads + X prefetch, 11: GEMM2 issue
+constexpr int kGroups = 3;                      // epilogue groups (4 warps each); chunk c is served by group c % kGroups
+constexpr int kWarpW1 = 2 + 4 * kGroups, kWarpMma2 = kWarpW1 + 1, kWarpX = kWarpW1 + 2;
+constexpr int kThreads = 32 * (kWarpX + 1);     // warp 0: H + W3 loads, 1: GEMM1 issue, 2..: epilogue, then W1 loads, GEMM2 issue, residual loads
 constexpr int K1 = 256, N1 = 1024, N2 = 256, CH = 64, NCH = N1 / CH;   // 16 chunks of 64 columns of Y
 constexpr int kHBytes = 4 * 128 * 128;          // H tile: 4 k-blocks x [128 rows x 128 B]
 constexpr int kB1Bytes = 4 * 32 * 128;          // W3 chunk half: 4 k-blocks x [32 rows x 128 B]
@@ -44,6 +57,11 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* b, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(b)), "r"(cta));
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync() {
@@ -114,6 +132,7 @@ struct Bars {
   uint64_t b2_full[kRing], b2_empty[kRing];
   uint64_t acc1_full[kAcc], acc1_empty[kAcc];
   uint64_t a2_full[kAcc], a2_empty[kAcc];
+  uint64_t xa_full[kAcc], a2_free[kAcc];
   uint64_t acc2_full, acc2_empty;
   uint32_t tmem_ptr, pad;
 };
@@ -145,10 +164,11 @@ fused_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       mbar_init(&bars->b2_full[s], 1); mbar_init(&bars->b2_empty[s], 1);
     }
     for (int b = 0; b < kAcc; ++b) {
-      mbar_init(&bars->acc1_full[b], 1); mbar_init(&bars->acc1_empty[b], 8);     // 4 warps x 2 CTAs
+      mbar_init(&bars->acc1_full[b], 1); mbar_init(&bars->acc1_empty[b], 8);     // 4 warps (one group) x 2 CTAs
       mbar_init(&bars->a2_full[b], 8);   mbar_init(&bars->a2_empty[b], 1);
+      mbar_init(&bars->xa_full[b], 1);   mbar_init(&bars->a2_free[b], 4);
     }
-    mbar_init(&bars->acc2_full, 1); mbar_init(&bars->acc2_empty, 16);            // 8 warps x 2 CTAs
+    mbar_init(&bars->acc2_full, 1); mbar_init(&bars->acc2_empty, 8 * kGroups);   // 4 kGroups warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -165,7 +185,7 @@ fused_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
 
   if (warp == 0) {
     // ============================== producer ==============================
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;                                 // tiles done by this pair
       uint32_t cc = 0;                            // chunk counter over the whole kernel (ring / buffer phases)
       for (int tile = pair; tile < g.tiles; tile += npairs, ++it) {
@@ -185,21 +205,12 @@ fused_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == kWarpW1) {
     // ============================== W1 producer (own thread: its ring must not stall the W3 ring) ==============================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t cc = 0;
       for (int tile = pair; tile < g.tiles; tile += npairs) {
-        // residual rows of this tile -> L2 a few chunks ahead of the epilogue's register loads (all at once would queue in
-        // front of the H / W3 loads the first GEMM waits for)
-        constexpr int kXAhead = 4;
-        const int xr0 = tile * 256 + (int)rank * 128;
-        auto prefetch_x = [&](int c) {
-          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&map_x), "r"(c * CH), "r"(xr0) : "memory");
-        };
-        for (int c = 0; c < kXAhead; ++c) prefetch_x(c);
         for (int c = 0; c < NCH; ++c, ++cc) {
-          if (c + kXAhead < NCH) prefetch_x(c + kXAhead);
           const int s = (int)(cc % kRing);
           // W1 rows [rank*128, +128) x K [c*64, +64) (B of GEMM2)
           mbar_wait(&bars->b2_empty[s], ((cc / kRing) & 1u) ^ 1u);
@@ -209,8 +220,8 @@ fused_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ============================== GEMM1 issuer (leader CTA; whole warp runs the loop, one elected lane issues) ==============================
-    if (rank == 0) {
+    // ============================== GEMM1 issuer (leader CTA, one elected thread) ==============================
+    if (rank == 0 && elect_one()) {
       constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);   // K-major, 128B swizzle, SBO 1024
       const uint32_t idesc1 = (1u << 4) | ((uint32_t)(CH >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);    // M 256, N 64
       auto lo = [&](const void* p) { return (uint64_t)((smem_u32(p) & 0x3FFFF) >> 4); };
@@ -228,17 +239,17 @@ fused_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           for (int kb = 0; kb < 4; ++kb) {
             const uint64_t a0 = lo(sH + kb * (128 * 128)), b0 = lo(sB1 + s * kB1Bytes + kb * (32 * 128));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma2_elect(d, kDescHi | (a0 + 2 * k), kDescHi | (b0 + 2 * k), idesc1, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma2(d, kDescHi | (a0 + 2 * k), kDescHi | (b0 + 2 * k), idesc1, (kb | k) ? 1u : 0u);
           }
-          commit_pair_elect(&bars->b1_empty[s]);
-          commit_pair_elect(&bars->acc1_full[b]);
+          commit_pair(&bars->b1_empty[s]);
+          commit_pair(&bars->acc1_full[b]);
         }
-        commit_pair_elect(&bars->h_empty);          // every GEMM1 of this tile is issued: H is free when they retire
+        commit_pair(&bars->h_empty);          // every GEMM1 of this tile is issued: H is free when they retire
       }
     }
-  } else if (warp == 11) {
-    // ============================== GEMM2 issuer (leader CTA) ==============================
-    if (rank == 0) {
+  } else if (warp == kWarpMma2) {
+    // ============================== GEMM2 issuer (leader CTA, one elected thread) ==============================
+    if (rank == 0 && elect_one()) {
       constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);    // M 256, N 256
       auto lo = [&](const void* p) { return (uint64_t)((smem_u32(p) & 0x3FFFF) >> 4); };
@@ -247,54 +258,69 @@ fused_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       for (int tile = pair; tile < g.tiles; tile += npairs, ++it) {
         for (int c = 0; c < NCH; ++c, ++cc) {
           const int s = (int)(cc % kRing), b = (int)(cc % kAcc);
-          if (it == 0 && lane == 0) TS(c * 4 + 0);
+          if (it == 0) TS(c * 4 + 0);
           mbar_wait(&bars->b2_full[s], (cc / kRing) & 1u);
-          if (it == 0 && lane == 0) TS(c * 4 + 1);
+          if (it == 0) TS(c * 4 + 1);
           mbar_wait_cluster(&bars->a2_full[b], (cc / kAcc) & 1u);
-          if (it == 0 && lane == 0) TS(c * 4 + 2);
+          if (it == 0) TS(c * 4 + 2);
           if (c == 0) mbar_wait_cluster(&bars->acc2_empty, ((uint32_t)it & 1u) ^ 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t a0 = lo(sA2 + b * kA2Bytes), b0 = lo(sB2 + s * kB2Bytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma2_elect(t_acc2, kDescHi | (a0 + 2 * k), kDescHi | (b0 + 2 * k), idesc2, (c | k) ? 1u : 0u);
-          commit_pair_elect(&bars->b2_empty[s]);
-          commit_pair_elect(&bars->a2_empty[b]);
-          if (it == 0 && lane == 0) TS(c * 4 + 3);
+          for (int k = 0; k < 4; ++k) umma2(t_acc2, kDescHi | (a0 + 2 * k), kDescHi | (b0 + 2 * k), idesc2, (c | k) ? 1u : 0u);
+          commit_pair(&bars->b2_empty[s]);
+          commit_pair(&bars->a2_empty[b]);
+          if (it == 0) TS(c * 4 + 3);
         }
-        commit_pair_elect(&bars->acc2_full);
+        commit_pair(&bars->acc2_full);
       }
     }
-  } else if (warp < 10) {
-    // ============================== epilogue ==============================
+  } else if (warp == kWarpX) {
+    // ============================== residual producer: X chunk -> the A2 buffer the epilogue will overwrite in place ==============================
+    if (elect_one()) {
+      // (an L2 prefetch of X running 8 chunks ahead of these loads was measured and changed nothing: the loads wait in the
+      // SM's TMA queue behind the W3 / W1 / Y traffic -- the kernel moves ~1.15 MB per CTA tile between L2 and the SM)
+      uint32_t cc = 0;
+      for (int tile = pair; tile < g.tiles; tile += npairs) {
+        const int xr0 = tile * 256 + (int)rank * 128;
+        for (int c = 0; c < NCH; ++c, ++cc) {
+          const int b = (int)(cc % kAcc);
+          const uint32_t ph = (cc / kAcc) & 1u;
+          mbar_wait(&bars->a2_empty[b], ph ^ 1u);            // GEMM2 of chunk cc - kAcc has read the buffer
+          mbar_wait(&bars->a2_free[b], ph ^ 1u);             // ... and so has the bulk store of that chunk
+          mbar_expect(&bars->xa_full[b], (uint32_t)kA2Bytes);
+          tma_2d(&map_x, &bars->xa_full[b], sA2 + b * kA2Bytes, c * CH, xr0);
+        }
+      }
+    }
+  } else {
+    // ============================== epilogue: kGroups x 4 warps ==============================
     const int q = warp & 3;                         // TMEM lane quarter = rows [32 q, +32) of my 128
-    const int grp = (warp - 2) >> 2;                // chunk parity this warp serves
+    const int grp = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int srow = q * 32 + lane;
     int it = 0;
     uint32_t cc0 = 0;                               // global chunk counter at the start of the current tile
     for (int tile = pair; tile < g.tiles; tile += npairs, ++it, cc0 += NCH) {
       const int row0 = tile * 256 + (int)rank * 128 + q * 32;
-      const int grow = row0 + lane;
-      const bool row_ok = grow < g.M;
-      const __half* xrow = xres + (size_t)(row_ok ? grow : 0) * g.x_ld;
-      // the residual row segment of a chunk (64 columns = 128 B) goes straight into registers, one chunk of this group ahead
-      uint32_t rcur[32], rnext[32];
-      if (row_ok) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ldg256(xrow + grp * CH + j * 16, rcur + 8 * j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) rcur[j] = 0;
-      }
-      for (int c = grp; c < NCH; c += 2) {
+      int pending = -1;                             // A2 buffer whose bulk store I issued and have not yet released
+      auto release = [&]() {
+        if (pending >= 0) {
+          if (elect_one()) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(&bars->a2_free[pending]);
+          }
+          __syncwarp();
+          pending = -1;
+        }
+      };
+      for (int c = grp; c < NCH; c += kGroups) {
         const uint32_t cc = cc0 + (uint32_t)c;
         const int b = (int)(cc % kAcc);
         const uint32_t ph = (cc / kAcc) & 1u;
-        if (c + 2 < NCH && row_ok) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ldg256(xrow + (c + 2) * CH + j * 16, rnext + 8 * j);
-        }
         const bool tr = trace && q == 0 && lane == 0 && it == 0;
         if (tr) dbg[64 + c * 8 + 0] = clock64() - t_origin;
+        release();
         mbar_wait(&bars->acc1_full[b], ph);
         if (tr) dbg[64 + c * 8 + 1] = clock64() - t_origin;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -305,20 +331,15 @@ fused_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (tr) dbg[64 + c * 8 + 2] = clock64() - t_origin;
-        if (lane == 0) mbar_arrive_remote(&bars->acc1_empty[b], 0);           // accumulator buffer back to the MMA warp
-        // A2 buffer b: GEMM2 of chunk cc - kAcc must have retired, and my own bulk store of that chunk must have read it
-        // (my store of chunk cc - 2 may still be in flight)
-        mbar_wait(&bars->a2_empty[b], ph ^ 1u);
+        if (lane == 0) mbar_arrive_remote(&bars->acc1_empty[b], 0);           // accumulator buffer back to the GEMM1 warp
+        mbar_wait(&bars->xa_full[b], ph);                                      // residual chunk has landed in A2 buffer b
         if (tr) dbg[64 + c * 8 + 3] = clock64() - t_origin;
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
-        if (tr) dbg[64 + c * 8 + 4] = clock64() - t_origin;
-        const int row = q * 32 + lane;
-        uint8_t* arow = sA2 + b * kA2Bytes + row * 128;
+        uint8_t* arow = sA2 + b * kA2Bytes + srow * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                                          // 8 chunks of 16 B = 8 columns each
-          const int sw = (j ^ (row & 7)) << 4;
-          const __half2* rh = reinterpret_cast<const __half2*>(&rcur[4 * j]);
+        for (int j = 0; j < 8; ++j) {                                          // 8 pieces of 16 B = 8 columns each, updated in place
+          uint4* pp = reinterpret_cast<uint4*>(arow + ((j ^ (srow & 7)) << 4));
+          const uint4 rr = *pp;
+          const __half2* rh = reinterpret_cast<const __half2*>(&rr);
           uint32_t o[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -328,31 +349,37 @@ fused_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
             const __half2 h = __floats2half2_rn(f0, f1);
             o[k] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          *reinterpret_cast<uint4*>(arow + sw) = make_uint4(o[0], o[1], o[2], o[3]);
+          *pp = make_uint4(o[0], o[1], o[2], o[3]);
         }
         if (tr) dbg[64 + c * 8 + 5] = clock64() - t_origin;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic writes -> visible to UMMA / TMA
         __syncwarp();
         if (tr) dbg[64 + c * 8 + 6] = clock64() - t_origin;
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_arrive_remote(&bars->a2_full[b], 0);
-          if (g.store_y) tma_store_2d(&map_y, sA2 + b * kA2Bytes + q * 32 * 128, c * CH, row0);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (g.store_y) {
+            tma_store_2d(&map_y, sA2 + b * kA2Bytes + q * 32 * 128, c * CH, row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          } else {
+            mbar_arrive(&bars->a2_free[b]);
+          }
         }
+        __syncwarp();
+        if (g.store_y) pending = b;
         if (tr) dbg[64 + c * 8 + 7] = clock64() - t_origin;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) rcur[j] = rnext[j];
       }
-      // ---- final epilogue: Z tile, 256 columns; warp (q, grp) takes columns [grp*128, +128)
+      release();
+      // ---- final epilogue: Z tile, 256 columns in 8 blocks of 32; block k goes to group k % kGroups
       mbar_wait(&bars->acc2_full, (uint32_t)it & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row = tile * 256 + (int)rank * 128 + q * 32 + lane;
-      for (int cb = 0; cb < 128; cb += 32) {
+      const int row = tile * 256 + (int)rank * 128 + srow;
+      constexpr int kLastBlk = 8 - kGroups;           // a group's last block index is >= this
+      for (int kblk = grp; kblk < 8; kblk += kGroups) {
         uint32_t v[32];
-        const int col = grp * 128 + cb;
+        const int col = kblk * 32;
         tmem_ld32(t_acc2 + lane_base + (uint32_t)col, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (cb + 32 >= 128) {
+        if (kblk >= kLastBlk) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(&bars->acc2_empty, 0);
@@ -372,7 +399,7 @@ fused_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         }
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
