@@ -11,6 +11,8 @@ python tools/conv_traffic.py gpurun_out/conv_traffic_r2.csv gpurun_out/r2_conv_t
 # the pair kernel inside the step: loc_1088 (launch 57), the 3x3x3 Mixed_5 layers, a 1024 -> 256 layer, and the 256 -> 1024 residual layer
 $NCU -k 'regex:conv_umma_persist_kernel' --set full --import-source on -s 64 -c 14 -o gpurun_out/prof_r2_persist -f $B > gpurun_out/p2.log 2>&1
 python tools/ncu_summary.py gpurun_out/prof_r2_persist.ncu-rep > gpurun_out/r2_ncu_conv_persist_pair.txt 2>&1
+$NCU -k 'regex:bottleneck_exit_kernel' --set full --import-source on -s 0 -c 3 -o gpurun_out/prof_r2_exit -f $B > gpurun_out/p4.log 2>&1
+python tools/ncu_summary.py gpurun_out/prof_r2_exit.ncu-rep > gpurun_out/r2_ncu_bottleneck_exit.txt 2>&1
 $NCU -k 'regex:conv_halo_kernel|clip_to_s2d|detect_' --set full -s 0 -c 3 -o gpurun_out/prof_r2_misc -f $B > gpurun_out/p3.log 2>&1
 python tools/ncu_summary.py gpurun_out/prof_r2_misc.ncu-rep > gpurun_out/r2_ncu_stem_s2d_detect.txt 2>&1
 python tools/conv_bench.py > gpurun_out/r2_conv_layers.txt 2>/dev/null
