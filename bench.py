@@ -144,6 +144,11 @@ def run_ours(args):
     if world > 1:
         gather = torch.empty((world, B, cap * 8 + 1), dtype=torch.float32, device=dev)
 
+    def mark(msg):
+        if getattr(args, "verbose", False):
+            print("[bench %.1fs] %s" % (time.time() - t_start, msg), file=sys.stderr, flush=True)
+    t_start = time.time()
+    mark("setup done")
     # eager step first: packs weights, counts the launches of one step (trunk, 3 refinement steps, detection)
     eager = step_b200.StepRunner(cfg, nets, B, W["T_in"], W["HW"], W["HW"], tubes, device=dev, use_graph=False, detect=DETECT)
     eager(clips_dev)
@@ -164,6 +169,7 @@ def run_ours(args):
                      "det": d0["det"][0].cpu().numpy().copy(), "cnt": int(d0["count"][0].item())}
         del cf0
     del hist0, eager
+    mark("eager step done, %d launches" % launches_per_step)
     # the public fast path: the whole step captured once into a CUDA graph (step_b200/runner.py)
     # args.inflight independent batches are kept in flight on separate streams (double buffering):
     # the H2D copy / small-grid layers of one batch overlap the other batch's kernels.
@@ -176,6 +182,7 @@ def run_ours(args):
             runners.append(step_b200.StepRunner(cfg, nets, B, W["T_in"], W["HW"], W["HW"], tubes, device=dev,
                                                 use_graph=not args.no_graph, detect=DETECT))
     torch.cuda.synchronize()
+    mark("graphs captured")
     turn = [0]
 
     def step(x):
@@ -252,6 +259,7 @@ def run_ours(args):
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
+    mark("timed regions done")
     # roofline of the dominant kernel class: replay exactly the conv launches of one step
     roof = None
     if rank == 0:
@@ -293,7 +301,9 @@ def run_ours(args):
             except Exception as ex:   # keep the eager replay if capture is refused
                 print("conv replay: graph capture failed (%s); timing eager launches" % ex, file=sys.stderr)
                 replay_fn = replay
+        mark("conv replay captured")
         ms_conv = timed_local(torch, replay_fn, max(3, args.steps))
+        mark("conv replay timed")
         pk = peaks()
         # algorithmic bytes of the same launches: input + weights + output (+ residual), fp16
         alg_bytes = 0
@@ -548,6 +558,7 @@ if __name__ == "__main__":
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying the CUDA graph")
     ap.add_argument("--inflight", type=int, default=3, help="independent batches kept in flight on separate streams")
+    ap.add_argument("--verbose", action="store_true", help="phase markers on stderr (to locate a stall)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

@@ -7,20 +7,18 @@
 //
 // As two launches of the implicit-GEMM kernel these cost 53 + 20 us at the C4 batch (M = 34496 rows): the first is bound by
 // reading its 1024-wide fp32 accumulator out of TMEM (K is only 256) and the second re-reads the 70 MB activation.  Here a CTA
-// PAIR (cta_group::2, 256 rows) walks the 1024 columns of Y in 16 chunks of 64: the residual chunk is TMA-loaded into a
-// shared-memory buffer in the K-major 128B-swizzled operand layout; GEMM1 chunk -> TMEM (64 columns, 4 buffers) -> epilogue
-// warps add the accumulator to the residual IN PLACE, ReLU, round to fp16 (the buffer is now the A operand of GEMM2 and is
-// also bulk-stored to Y) -> GEMM2 accumulates Z += Y_chunk * W1[:, chunk]^T in a second TMEM region (256 columns).  Y is
-// rounded to fp16 before GEMM2 exactly as the two-launch path rounds it, and both GEMMs accumulate K in the same order as the
-// library kernel (64-wide k-blocks), so the results are bit-identical to the unfused path (tests/test_gpu_conv.py).
+// PAIR (cta_group::2, 256 rows) walks the 1024 columns of Y in 16 chunks of 64: GEMM1 chunk -> TMEM (64 columns, 4 buffers) ->
+// epilogue warps add the residual, ReLU, round to fp16 and write the chunk as a K-major 128B-swizzled A operand into shared
+// memory (the same bytes are bulk-stored to Y) -> GEMM2 accumulates Z += Y_chunk * W1[:, chunk]^T in a second TMEM region
+// (256 columns).  Y is rounded to fp16 before GEMM2 exactly as the two-launch path rounds it, and both GEMMs accumulate K in
+// the same order as the library kernel (64-wide k-blocks), so the results are bit-identical to the unfused path.
 //
-// Per CTA (17 warps): warp 0 loads H and the W3 chunks, warp 1 issues GEMM1 (leader CTA), warps 2-13 are three epilogue groups
-// (chunk c -> group c % 3), warp 14 loads the W1 slices, warp 15 issues GEMM2, warp 16 loads the residual chunks.
-// Lessons measured while building it (tools/probe/fused_exit_probe.cu keeps the history and a cycle trace): a shared W3 / W1
+// Per CTA (384 threads): warp 0 loads H and the W3 chunks (TMA), warp 1 issues GEMM1 (leader CTA), warps 2-5 / 6-9 are the
+// epilogue groups of the even / odd chunks, warp 10 loads the W1 slices and prefetches the residual into L2, warp 11 issues
+// GEMM2.  Lessons measured while building it (tools/probe/fused_exit_probe.cu, tools/experiments/README.md): a shared W3 / W1
 // producer thread serialises the two rings; `mbarrier.arrive.release.cluster` compiles to MEMBAR.ALL.GPU and waits for every
-// outstanding global load of the thread (2-4k cycles); tcgen05 / TMA instructions inside a divergent `lane == 0` branch get
-// an R2UR / ELECT loop each (~90 cycles, which paces N = 64 MMAs) while `if (elect_one())` keeps the operands in uniform
-// registers.  Bound: ~1.15 MB per CTA tile between L2 and the SM (310 MB per launch at the C4 batch).
+// outstanding global load of the thread (2-4k cycles); MMAs issued from inside a divergent `lane == 0` branch cost ~90 cycles
+// each (R2UR / ELECT loops), which paces N = 64 MMAs -- the issuing warps stay convergent and elect per instruction.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -30,9 +28,7 @@
 namespace step {
 namespace bexit {
 
-constexpr int kGroups = 3;                      // epilogue groups (4 warps each); chunk c is served by group c % kGroups
-constexpr int kWarpW1 = 2 + 4 * kGroups, kWarpMma2 = kWarpW1 + 1, kWarpX = kWarpW1 + 2;
-constexpr int kThreads = 32 * (kWarpX + 1);     // warp 0: H + W3 loads, 1: GEMM1 issue, 2..: epilogue, then W1 loads, GEMM2 issue, residual loads
+constexpr int kThreads = 384;                   // warp 0: H + W3 loads, 1: GEMM1 issue, 2-9: epilogue, 10: W1 loads + X prefetch, 11: GEMM2 issue
 constexpr int K1 = 256, N1 = 1024, N2 = 256, CH = 64, NCH = N1 / CH;   // 16 chunks of 64 columns of Y
 constexpr int kHBytes = 4 * 128 * 128;          // H tile: 4 k-blocks x [128 rows x 128 B]
 constexpr int kB1Bytes = 4 * 32 * 128;          // W3 chunk half: 4 k-blocks x [32 rows x 128 B]
@@ -55,11 +51,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* b, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(b)), "r"(cta));
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync() {
@@ -130,7 +121,6 @@ struct Bars {
   uint64_t b2_full[kRing], b2_empty[kRing];
   uint64_t acc1_full[kAcc], acc1_empty[kAcc];
   uint64_t a2_full[kAcc], a2_empty[kAcc];
-  uint64_t xa_full[kAcc], a2_free[kAcc];
   uint64_t acc2_full, acc2_empty;
   uint32_t tmem_ptr, pad;
 };
@@ -159,11 +149,10 @@ bottleneck_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_c
       mbar_init(&bars->b2_full[s], 1); mbar_init(&bars->b2_empty[s], 1);
     }
     for (int b = 0; b < kAcc; ++b) {
-      mbar_init(&bars->acc1_full[b], 1); mbar_init(&bars->acc1_empty[b], 8);     // 4 warps (one group) x 2 CTAs
+      mbar_init(&bars->acc1_full[b], 1); mbar_init(&bars->acc1_empty[b], 8);     // 4 warps x 2 CTAs
       mbar_init(&bars->a2_full[b], 8);   mbar_init(&bars->a2_empty[b], 1);
-      mbar_init(&bars->xa_full[b], 1);   mbar_init(&bars->a2_free[b], 4);
     }
-    mbar_init(&bars->acc2_full, 1); mbar_init(&bars->acc2_empty, 8 * kGroups);   // 4 kGroups warps x 2 CTAs
+    mbar_init(&bars->acc2_full, 1); mbar_init(&bars->acc2_empty, 16);            // 8 warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -184,7 +173,7 @@ bottleneck_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_c
 
   if (warp == 0) {
     // ============================== producer ==============================
-    if (elect_one()) {
+    if (lane == 0) {
       int it = 0;                                 // tiles done by this pair
       uint32_t cc = 0;                            // chunk counter over the whole kernel (ring / buffer phases)
       for (int tile = pair; tile < g.tiles; tile += npairs, ++it) {
@@ -204,12 +193,21 @@ bottleneck_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_c
         }
       }
     }
-  } else if (warp == kWarpW1) {
+  } else if (warp == 10) {
     // ============================== W1 producer (own thread: its ring must not stall the W3 ring) ==============================
-    if (elect_one()) {
+    if (lane == 0) {
       uint32_t cc = 0;
       for (int tile = pair; tile < g.tiles; tile += npairs) {
+        // residual rows of this tile -> L2 a few chunks ahead of the epilogue's register loads (all at once would queue in
+        // front of the H / W3 loads the first GEMM waits for)
+        constexpr int kXAhead = 4;
+        const int xr0 = tile * 256 + (int)rank * 128;
+        auto prefetch_x = [&](int c) {
+          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&map_x), "r"(c * CH), "r"(xr0) : "memory");
+        };
+        for (int c = 0; c < kXAhead; ++c) prefetch_x(c);
         for (int c = 0; c < NCH; ++c, ++cc) {
+          if (c + kXAhead < NCH) prefetch_x(c + kXAhead);
           const int s = (int)(cc % kRing);
           // W1 rows [rank*128, +128) x K [c*64, +64) (B of GEMM2)
           mbar_wait(&bars->b2_empty[s], ((cc / kRing) & 1u) ^ 1u);
@@ -219,8 +217,8 @@ bottleneck_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ============================== GEMM1 issuer (leader CTA, one elected thread) ==============================
-    if (rank == 0 && elect_one()) {
+    // ============================== GEMM1 issuer (leader CTA; whole warp runs the loop, one elected lane issues) ==============================
+    if (rank == 0) {
       constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);   // K-major, 128B swizzle, SBO 1024
       const uint32_t idesc1 = (1u << 4) | ((uint32_t)(CH >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);    // M 256, N 64
       auto lo = [&](const void* p) { return (uint64_t)((smem_u32(p) & 0x3FFFF) >> 4); };
@@ -238,17 +236,17 @@ bottleneck_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_c
           for (int kb = 0; kb < 4; ++kb) {
             const uint64_t a0 = lo(sH + kb * (128 * 128)), b0 = lo(sB1 + s * kB1Bytes + kb * (32 * 128));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma2(d, kDescHi | (a0 + 2 * k), kDescHi | (b0 + 2 * k), idesc1, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma2_elect(d, kDescHi | (a0 + 2 * k), kDescHi | (b0 + 2 * k), idesc1, (kb | k) ? 1u : 0u);
           }
-          commit_pair(&bars->b1_empty[s]);
-          commit_pair(&bars->acc1_full[b]);
+          commit_pair_elect(&bars->b1_empty[s]);
+          commit_pair_elect(&bars->acc1_full[b]);
         }
-        commit_pair(&bars->h_empty);          // every GEMM1 of this tile is issued: H is free when they retire
+        commit_pair_elect(&bars->h_empty);          // every GEMM1 of this tile is issued: H is free when they retire
       }
     }
-  } else if (warp == kWarpMma2) {
-    // ============================== GEMM2 issuer (leader CTA, one elected thread) ==============================
-    if (rank == 0 && elect_one()) {
+  } else if (warp == 11) {
+    // ============================== GEMM2 issuer (leader CTA) ==============================
+    if (rank == 0) {
       constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);    // M 256, N 256
       auto lo = [&](const void* p) { return (uint64_t)((smem_u32(p) & 0x3FFFF) >> 4); };
@@ -263,57 +261,42 @@ bottleneck_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_c
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t a0 = lo(sA2 + b * kA2Bytes), b0 = lo(sB2 + s * kB2Bytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma2(t_acc2, kDescHi | (a0 + 2 * k), kDescHi | (b0 + 2 * k), idesc2, (c | k) ? 1u : 0u);
-          commit_pair(&bars->b2_empty[s]);
-          commit_pair(&bars->a2_empty[b]);
+          for (int k = 0; k < 4; ++k) umma2_elect(t_acc2, kDescHi | (a0 + 2 * k), kDescHi | (b0 + 2 * k), idesc2, (c | k) ? 1u : 0u);
+          commit_pair_elect(&bars->b2_empty[s]);
+          commit_pair_elect(&bars->a2_empty[b]);
         }
-        commit_pair(&bars->acc2_full);
+        commit_pair_elect(&bars->acc2_full);
       }
     }
-  } else if (warp == kWarpX) {
-    // ============================== residual producer: X chunk -> the A2 buffer the epilogue will overwrite in place ==============================
-    if (elect_one()) {
-      // (an L2 prefetch of X running 8 chunks ahead of these loads was measured and changed nothing: the loads wait in the
-      // SM's TMA queue behind the W3 / W1 / Y traffic -- the kernel moves ~1.15 MB per CTA tile between L2 and the SM)
-      uint32_t cc = 0;
-      for (int tile = pair; tile < g.tiles; tile += npairs) {
-        const int xr0 = tile * 256 + (int)rank * 128;
-        for (int c = 0; c < NCH; ++c, ++cc) {
-          const int b = (int)(cc % kAcc);
-          const uint32_t ph = (cc / kAcc) & 1u;
-          mbar_wait(&bars->a2_empty[b], ph ^ 1u);            // GEMM2 of chunk cc - kAcc has read the buffer
-          mbar_wait(&bars->a2_free[b], ph ^ 1u);             // ... and so has the bulk store of that chunk
-          mbar_expect(&bars->xa_full[b], (uint32_t)kA2Bytes);
-          tma_2d(&map_x, &bars->xa_full[b], sA2 + b * kA2Bytes, c * CH, xr0);
-        }
-      }
-    }
-  } else {
-    // ============================== epilogue: kGroups x 4 warps ==============================
+  } else if (warp < 10) {
+    // ============================== epilogue ==============================
     const int q = warp & 3;                         // TMEM lane quarter = rows [32 q, +32) of my 128
-    const int grp = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 2;                // chunk parity this warp serves
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const int srow = q * 32 + lane;
     int it = 0;
     uint32_t cc0 = 0;                               // global chunk counter at the start of the current tile
     for (int tile = pair; tile < g.tiles; tile += npairs, ++it, cc0 += NCH) {
       const int row0 = tile * 256 + (int)rank * 128 + q * 32;
-      int pending = -1;                             // A2 buffer whose bulk store I issued and have not yet released
-      auto release = [&]() {
-        if (pending >= 0) {
-          if (elect_one()) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            mbar_arrive(&bars->a2_free[pending]);
-          }
-          __syncwarp();
-          pending = -1;
-        }
-      };
-      for (int c = grp; c < NCH; c += kGroups) {
+      const int grow = row0 + lane;
+      const bool row_ok = grow < g.M;
+      const __half* xrow = xres + (size_t)(row_ok ? grow : 0) * g.x_ld;
+      // the residual row segment of a chunk (64 columns = 128 B) goes straight into registers, one chunk of this group ahead
+      uint32_t rcur[32], rnext[32];
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ldg256(xrow + grp * CH + j * 16, rcur + 8 * j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rcur[j] = 0;
+      }
+      for (int c = grp; c < NCH; c += 2) {
         const uint32_t cc = cc0 + (uint32_t)c;
         const int b = (int)(cc % kAcc);
         const uint32_t ph = (cc / kAcc) & 1u;
-        release();
+        if (c + 2 < NCH && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ldg256(xrow + (c + 2) * CH + j * 16, rnext + 8 * j);
+        }
         mbar_wait(&bars->acc1_full[b], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t v[64];
@@ -322,14 +305,18 @@ bottleneck_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_c
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(&bars->acc1_empty[b], 0);           // accumulator buffer back to the GEMM1 warp
-        mbar_wait(&bars->xa_full[b], ph);                                      // residual chunk has landed in A2 buffer b
-        uint8_t* arow = sA2 + b * kA2Bytes + srow * 128;
+        if (lane == 0) mbar_arrive_remote(&bars->acc1_empty[b], 0);           // accumulator buffer back to the MMA warp
+        // A2 buffer b: GEMM2 of chunk cc - kAcc must have retired, and my own bulk store of that chunk must have read it
+        // (my store of chunk cc - 2 may still be in flight)
+        mbar_wait(&bars->a2_empty[b], ph ^ 1u);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const int row = q * 32 + lane;
+        uint8_t* arow = sA2 + b * kA2Bytes + row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                                          // 8 pieces of 16 B = 8 columns each, updated in place
-          uint4* pp = reinterpret_cast<uint4*>(arow + ((j ^ (srow & 7)) << 4));
-          const uint4 rr = *pp;
-          const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+        for (int j = 0; j < 8; ++j) {                                          // 8 chunks of 16 B = 8 columns each
+          const int sw = (j ^ (row & 7)) << 4;
+          const __half2* rh = reinterpret_cast<const __half2*>(&rcur[4 * j]);
           uint32_t o[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -339,34 +326,28 @@ bottleneck_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_c
             const __half2 h = __floats2half2_rn(f0, f1);
             o[k] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          *pp = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(arow + sw) = make_uint4(o[0], o[1], o[2], o[3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic writes -> visible to UMMA / TMA
         __syncwarp();
-        if (elect_one()) {
+        if (lane == 0) {
           mbar_arrive_remote(&bars->a2_full[b], 0);
-          if (g.store_y) {
-            tma_store_2d(&map_y, sA2 + b * kA2Bytes + q * 32 * 128, c * CH, row0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          } else {
-            mbar_arrive(&bars->a2_free[b]);
-          }
+          if (g.store_y) tma_store_2d(&map_y, sA2 + b * kA2Bytes + q * 32 * 128, c * CH, row0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        __syncwarp();
-        if (g.store_y) pending = b;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rcur[j] = rnext[j];
       }
-      release();
-      // ---- final epilogue: Z tile, 256 columns in 8 blocks of 32; block k goes to group k % kGroups
+      // ---- final epilogue: Z tile, 256 columns; warp (q, grp) takes columns [grp*128, +128)
       mbar_wait(&bars->acc2_full, (uint32_t)it & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row = tile * 256 + (int)rank * 128 + srow;
-      constexpr int kLastBlk = 8 - kGroups;           // a group's last block index is >= this
-      for (int kblk = grp; kblk < 8; kblk += kGroups) {
+      const int row = tile * 256 + (int)rank * 128 + q * 32 + lane;
+      for (int cb = 0; cb < 128; cb += 32) {
         uint32_t v[32];
-        const int col = kblk * 32;
+        const int col = grp * 128 + cb;
         tmem_ld32(t_acc2 + lane_base + (uint32_t)col, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (kblk >= kLastBlk) {
+        if (cb + 32 >= 128) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(&bars->acc2_empty, 0);
@@ -386,7 +367,7 @@ bottleneck_exit_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_c
         }
       }
     }
-    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

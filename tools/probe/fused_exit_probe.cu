@@ -21,6 +21,10 @@
 //   50 us  residual through registers with a staggered L2 prefetch; GEMM1 and GEMM2 issued by separate warps
 //   62 us  16 half-chunk epilogue warps storing Y with st.global (slower: 64-byte row pieces instead of full-line bulk stores)
 //   47 us  THIS FILE: residual TMA-loaded into the A2 buffer, updated in place; 3 epilogue groups (96 registers / thread)
+// OPEN ISSUE: this variant (and only this one) stalls inside bench.py as soon as a second batch is in flight on another
+// stream, or when it asks for the full 227 KB of shared memory -- with or without CUDA graphs and programmatic dependent launch
+// (tools/experiments/r2_fused_hang.sh); every single-stream test, the 34496-row bit-exactness tests included, passes.  The 50 us
+// variant passes the same matrix and is the one in libstep_b200.so (step_b200/csrc/bottleneck_exit.cu).
 // What bounds it now: ~1.15 MB per CTA tile moves between L2 and the SM (W3 + W1 halves 512 KB, X 256 KB, Y 256 KB, H + Z
 // 128 KB) = 310 MB per launch, and every TMA load waits 2-3 us in the SM's queue under that load.
 #include <cuda.h>
