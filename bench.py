@@ -148,6 +148,9 @@ def run_ours(args):
         if getattr(args, "verbose", False):
             print("[bench %.1fs] %s" % (time.time() - t_start, msg), file=sys.stderr, flush=True)
     t_start = time.time()
+    if getattr(args, "verbose", False):   # a stalled run prints where every Python thread is after 40 s
+        import faulthandler
+        faulthandler.dump_traceback_later(40, exit=False, file=sys.stderr)
     mark("setup done")
     # eager step first: packs weights, counts the launches of one step (trunk, 3 refinement steps, detection)
     eager = step_b200.StepRunner(cfg, nets, B, W["T_in"], W["HW"], W["HW"], tubes, device=dev, use_graph=False, detect=DETECT)
@@ -247,11 +250,14 @@ def run_ours(args):
         sampler.start()
     for _ in range(args.warmup):
         step(clips_dev)
+    mark("warm-up enqueued")
     ms = timed(lambda: step(clips_dev), args.steps)
+    mark("device-resident region timed")
     launches = launches_per_step * args.steps
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    mark("end-to-end region timed")
     if rank == 0 and len(sampler.rows) < 3:   # keep the GPU busy until nvidia-smi has delivered a few samples
         t_end = time.time() + 1.0
         while time.time() < t_end:

@@ -35,10 +35,14 @@ inline cudaStream_t cu(step_stream_t s) { return reinterpret_cast<cudaStream_t>(
     }                                                                               \
   } while (0)
 
-// STEP_B200_PDL=0 launches the conv kernels without programmatic dependent launch (A/B timing)
+// Programmatic dependent launch of the conv kernels is OPT-IN (STEP_B200_PDL=1).  It is worth ~3 % (conv class 3.63 -> 3.55 ms
+// per step), but with three batches in flight (graphs on three streams + the pinned-host H2D copies of the end-to-end region) one
+// bench.py run in eight stalled in a stream that never drained (4 of 33 runs with it, 0 of 12 without; tools/experiments/
+// r2_fused_stress.sh).  The cause was not found -- every kernel allocates its TMEM before it triggers its dependents -- so the
+// default is the configuration that never stalled.
 inline bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("STEP_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("STEP_B200_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
 

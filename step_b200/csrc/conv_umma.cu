@@ -320,15 +320,14 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 
 // ---- CTA-pair (cta_group::2) protocol helpers; validated by tools/probe/umma_2cta_probe.cu and conv_pair_probe*.cu ----
-// wait on a barrier whose arrivals come from both CTAs of the pair. Default (CTA-scope) semantics on both sides, as the data
-// guarded here lives in TMEM / shared memory and is ordered by the tcgen05 / proxy fences: the cluster-scope forms compile to
-// MEMBAR.ALL.GPU (arrive) and CCTL.IVALL (wait), which stall on every outstanding global load of the thread (measured in
-// tools/probe/fused_exit_probe.cu: 2-4k cycles per arrive).
+// wait with cluster-scope acquire: the arrivals come from both CTAs of the pair.  (The CTA-scope forms -- a bare SYNCS.ARRIVE
+// instead of MEMBAR.ALL.GPU + arrive -- were measured here as well: no difference for this kernel, whose epilogue arrives once per
+// tile with nothing in flight; the fused bottleneck exit, which arrives per 64-column chunk with loads in flight, needs them.)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAITC_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra.uni WAITC_DONE;\n\t"
       "bra.uni WAITC_LOOP;\n\t"
       "WAITC_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
@@ -337,7 +336,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 // TMA loads of a CTA pair: the data lands in the issuing CTA's shared memory, the bytes are signalled on the LEADER's
 // barrier (same offset, CTA-rank bit of the shared::cluster address cleared)
