@@ -37,12 +37,16 @@ WORKLOAD = dict(B=8, T_in=32, HW=224, N=11, max_iter=3)
 DETECT = dict(conf_thresh=0.01, nms_thresh=0.4, topk=300)
 
 
+CONV_CLASS_SOURCES = ("bottleneck_exit.cu", "common.cuh", "conv_halo.cu", "conv_umma.cu", "umma_ptx.cuh")
+
+
 def csrc_sha():
-    """Hash of the kernel sources, to tie profiles/*.json captures to the build they were taken from."""
+    """Hash of the sources of the tcgen05 conv class (the kernels whose DRAM traffic profiles/r2_conv_traffic.json holds), to tie
+    that capture to the build it was taken from; edits to the other kernels do not invalidate it."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "step_b200", "csrc")
-    for f in sorted(os.listdir(d)):
+    for f in CONV_CLASS_SOURCES:
         h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 

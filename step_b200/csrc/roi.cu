@@ -550,12 +550,12 @@ extern "C" int step_roi_align_fwd_nhwc(const void* feat, int dtype, int K, int H
   FrameMap fm{roi_T, feat_T, t_start};
   if (dtype == STEP_F16 && exact == 0 && (size_t)ph * pw * sizeof(MergedBin) <= 48 * 1024 &&
       (long long)H * W * feat_ld < (1LL << 31)) {   // table entries hold 32-bit element offsets inside one frame
-    // few ROI rows (the pipeline pools 704 per step): split every row over up to 4 CTAs by channel range
+    // One CTA per ROI row.  Splitting a row's channels over several CTAs (STEP_B200_ROI_PARTS=2|4, kept for A/B) was measured on
+    // the 704-row in-pipeline call and is slower (45 -> 59 us): every part rebuilds the row's tap table.
     int parts = 1;
-    {
-      const int nvec = C / 8, hv = (nvec & 1) == 0 ? nvec / 2 : nvec;
-      while (false && parts < 4 && (long long)R * parts < 16 * kNumSMs && hv % (parts * 2) == 0 && nvec % (parts * 2) == 0) parts *= 2;
-      if (const char* e = getenv("STEP_B200_ROI_PARTS")) { const int v = atoi(e); if (v >= 1 && hv % v == 0 && nvec % v == 0) parts = v; }
+    if (const char* e = getenv("STEP_B200_ROI_PARTS")) {
+      const int nvec = C / 8, hv = (nvec & 1) == 0 ? nvec / 2 : nvec, v = atoi(e);
+      if (v >= 1 && hv % v == 0 && nvec % v == 0) parts = v;
     }
     roi_align_fwd_nhwc_f16_packed_kernel<<<dim3(R, parts), 128 * (parts > 1 ? 1 : 2), (size_t)ph * pw * sizeof(MergedBin), cu(stream)>>>(
         (const __half*)feat, H, W, C, feat_ld, rois, scale, ph, pw, sampling_ratio, (__half*)out, out_ld, fm);
