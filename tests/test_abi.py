@@ -51,3 +51,20 @@ def test_ops_raise_without_cuda_tensor():
     with pytest.raises(RuntimeError):
         roi_layers.roi_align(x, torch.zeros(1, 5), (7, 7), 1 / 16., 0)
     assert roi_layers.nms(torch.zeros(0, 4), torch.zeros(0), 0.4).numel() == 0  # empty in -> empty out, nms.h:41
+
+
+def test_argument_errors_are_reported_before_any_device_work():
+    """The entry points validate their arguments first (STEP_E_ARG + step_last_error text), the role AT_ASSERTM plays in
+    the reference's ops: checked here without a GPU on the fused bottleneck exit, which exists for the reference's head
+    widths only (two_branch.py:190-192)."""
+    import ctypes
+    from step_b200 import _lib
+    lib = _lib.lib()
+    buf = (ctypes.c_char * 4096)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    rc = lib.step_bottleneck_exit_f16(p, 128, p, p, 1024, p, None, 1, None, 0, p, 256, 64, 128, 1024, 256, None)
+    assert rc == 10001                                        # STEP_E_ARG
+    lib.step_last_error.restype = ctypes.c_char_p
+    assert b"planes 256" in lib.step_last_error()
+    rc = lib.step_bottleneck_exit_f16(None, 256, p, p, 1024, p, None, 1, None, 0, p, 256, 64, 256, 1024, 256, None)
+    assert rc == 10001 and b"null pointer" in lib.step_last_error()
