@@ -109,3 +109,22 @@ def test_compat_patch_substitutes_the_names_the_reference_drivers_import():
             if k not in saved:
                 del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_fused_exit_barrier_protocol_survives_adversarial_interleavings():
+    """tools/protocol_sim.py replays the mbarrier protocol of the fused bottleneck-exit kernel (csrc/bottleneck_exit.cu: TMA
+    producers, two MMA-issuing threads, eight epilogue warps per CTA of the pair, asynchronous commit / complete_tx
+    deliveries) under random and skewed schedules: no schedule may end blocked (a deadlock or a parity overrun)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "protocol_sim", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "protocol_sim.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    slow_cta = lambda n: isinstance(n, tuple) and len(n) > 1 and n[1] == 1
+    for skew in (None, slow_cta):
+        for p_deliver in (0.25, 0.0):
+            for store_y in (True, False):
+                for seed in range(4):
+                    res, info = sim.simulate("v3", seed, tiles=2, store_y=store_y, skew=skew, p_deliver=p_deliver)
+                    assert res == "ok", (res, info)
