@@ -128,3 +128,26 @@ def test_fused_exit_barrier_protocol_survives_adversarial_interleavings():
                 for seed in range(4):
                     res, info = sim.simulate("v3", seed, tiles=2, store_y=store_y, skew=skew, p_deliver=p_deliver)
                     assert res == "ok", (res, info)
+
+
+def test_fused_exit_dispatch_rule():
+    """engine.can_fuse_exit: the one-launch block exit is used for the reference's head widths on the fp16 inference path only;
+    the training forward (tape recording) and every other width keep the per-layer launches."""
+    from step_b200 import _lib as L
+    from step_b200 import engine as E
+    assert E.can_fuse_exit(L.F16, 256, 1024, 256)
+    assert not E.can_fuse_exit(L.F32, 256, 1024, 256)
+    assert not E.can_fuse_exit(L.F16, 128, 1024, 256)
+    assert not E.can_fuse_exit(L.F16, 256, 1024, 512)
+    old = E.TAPE
+    try:
+        E.TAPE = []
+        assert not E.can_fuse_exit(L.F16, 256, 1024, 256)
+    finally:
+        E.TAPE = old
+    old = E.FUSE_EXIT
+    try:
+        E.FUSE_EXIT = False
+        assert not E.can_fuse_exit(L.F16, 256, 1024, 256)
+    finally:
+        E.FUSE_EXIT = old
